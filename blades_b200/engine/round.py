@@ -1,0 +1,303 @@
+"""The per-rank round engine: local training of this rank's virtual clients, attack
+phase, robust aggregation, server step.  Replaces the reference's
+``Simulator.train_actor`` + ``_RayActor.local_training`` pipeline
+(/root/reference/src/blades/simulator.py:203-245, actor.py:23-33):
+
+reference (per round)                          | here
+-----------------------------------------------+------------------------------------------
+pickle global model + N client objects to Ray   | nothing moves: theta[d] is device resident
+actors                                          | and replicated on every rank
+per client: load_state_dict, clone params,      | fedsgd: ONE batched fwd/bwd for all local
+k SGD steps, 2x flat concat to CPU              | clients, wgrad epilogue writes the update
+                                                | row; fedavg/custom: time-sliced on a shared
+                                                | worker model, one fused diff kernel per client
+gather N CPU vectors, torch.stack               | rows already sit in U_g[n_local, d]
+                                                | (NVLink-addressable symmetric memory)
+f attacker callbacks on CPU                     | virtual rows inside the aggregation kernel
+aggregator on CPU [N,d]                         | fused pull-mode kernels / tcgen05 Gram
+per-param python loop + optimizer.step          | theta += lr*agg in the kernel epilogue
+"""
+from __future__ import annotations
+
+import copy
+import logging
+import time
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ..client import BladesClient, ByzantineClient
+from ..comm.group import World, split_clients
+from ..parallel.matrix import LocalMatrix, UpdateMatrix, VirtualRows
+from ..server import BladesServer, _is_plain_sgd
+from . import batched as cb
+from .flat import FlatParams
+
+__all__ = ["RoundEngine", "PhaseTimer"]
+
+
+class PhaseTimer:
+    """CUDA-event (or wall-clock on CPU) timing of the round phases."""
+
+    def __init__(self, device: torch.device, enabled: bool = True):
+        self.cuda = device.type == "cuda"
+        self.enabled = enabled
+        self.records: List[Dict[str, float]] = []
+        self._cur: Dict[str, tuple] = {}
+
+    def start(self, name: str):
+        if not self.enabled:
+            return
+        if self.cuda:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._cur[name] = (ev, None)
+        else:
+            self._cur[name] = (time.perf_counter(), None)
+
+    def stop(self, name: str):
+        if not self.enabled or name not in self._cur:
+            return
+        beg, _ = self._cur[name]
+        if self.cuda:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._cur[name] = (beg, ev)
+        else:
+            self._cur[name] = (beg, time.perf_counter())
+
+    def flush(self) -> Dict[str, float]:
+        out = {}
+        if self.cuda and self._cur:
+            torch.cuda.synchronize()
+        for k, (b, e) in self._cur.items():
+            if e is None:
+                continue
+            out[k] = b.elapsed_time(e) if self.cuda else (e - b) * 1e3
+        self._cur = {}
+        if out:
+            self.records.append(out)
+        return out
+
+
+def _overrides(obj, name: str, base=BladesClient) -> bool:
+    return getattr(type(obj), name) is not getattr(base, name)
+
+
+def _fusable_classes():
+    from ..attackers.alieclient import AlieClient
+    from ..attackers.ipmclient import IpmClient
+    return (AlieClient, IpmClient)
+
+
+class RoundEngine:
+    def __init__(self, world: World, dataset, clients: Sequence[BladesClient], device: torch.device,
+                 use_kernels: Optional[bool] = None, profile: bool = False):
+        self.world = world
+        self.dataset = dataset
+        self.clients = list(clients)
+        self.device = torch.device(device)
+        self.n_total = len(self.clients)
+        parts = split_clients(self.n_total, world.size)
+        self.local_idx = [int(i) for i in parts[world.rank]]
+        self.row_of = {gi: r for r, gi in enumerate(self.local_idx)}
+        self.shard_sizes = [len(p) for p in parts]
+        self.use_kernels = (self.device.type == "cuda") if use_kernels is None else use_kernels
+        self.timer = PhaseTimer(self.device, enabled=profile)
+        self.debug_logger = logging.getLogger("debug")
+        self.server: Optional[BladesServer] = None
+        self.gflat: Optional[FlatParams] = None
+        self.worker: Optional[nn.Module] = None
+        self.wflat: Optional[FlatParams] = None
+        self.U: Optional[torch.Tensor] = None
+        self.matrix_factory: Optional[Callable] = None
+        self.last_client_losses: Optional[torch.Tensor] = None
+        self.kernel_launches = 0
+        self._stage = None          # (device X, device y) staged for the next round (prefetch)
+
+    # ------------------------------------------------------------------ setup
+    def setup(self, model: nn.Module, server_opt, aggregator, loss: str, client_lr: float,
+              client_optimizer="SGD", server_lr: float = 0.1) -> BladesServer:
+        model.to(self.device)
+        self.gflat = FlatParams(model, device=self.device)
+        if server_opt == "SGD" or server_opt is None:
+            server_opt = torch.optim.SGD(model.parameters(), lr=server_lr)
+        self.server = BladesServer(optimizer=server_opt, model=model, aggregator=aggregator, flat=self.gflat)
+        self.worker = copy.deepcopy(model)
+        self.wflat = FlatParams(self.worker, device=self.device)
+        self.client_opt_spec = client_optimizer
+        self.worker_opt = torch.optim.SGD(self.worker.parameters(), lr=client_lr)
+        d = self.gflat.numel
+        self.d = d
+        self._alloc_updates(len(self.local_idx), d)
+        for c in self.clients:
+            c.set_loss(loss)
+            c.device = self.device
+        for gi in self.local_idx:
+            self.clients[gi].bind_row(self.U, self.row_of[gi])
+        self.batchable_model = cb.is_batchable(model)
+        return self.server
+
+    def _alloc_updates(self, n_local: int, d: int) -> None:
+        if self.world.distributed and self.device.type == "cuda":
+            from ..comm import symm
+            self.symm = symm.SymmetricUpdates(self.world, self.shard_sizes, d)
+            self.U = self.symm.local
+        else:
+            self.symm = None
+            self.U = torch.zeros(max(n_local, 1), d, device=self.device, dtype=torch.float32)[:n_local]
+
+    # ------------------------------------------------------------------ training
+    def _stock_for_batching(self, c: BladesClient) -> bool:
+        return not (_overrides(c, "local_training") or _overrides(c, "on_train_round_begin")
+                    or _overrides(c, "on_train_round_end") or _overrides(c, "set_para")
+                    or _overrides(c, "_post_backward") and not hasattr(c, "grad_sign"))
+
+    def train_local(self, local_steps: int, lr: float) -> None:
+        """Fill U[r] for every local client r."""
+        local = [self.clients[gi] for gi in self.local_idx]
+        plain = self.client_opt_spec in ("SGD", None, torch.optim.SGD)
+        batch_rows, slice_rows = [], []
+        for r, c in enumerate(local):
+            if local_steps == 1 and plain and self.batchable_model and self._stock_for_batching(c):
+                batch_rows.append(r)
+            else:
+                slice_rows.append(r)
+        if batch_rows:
+            try:
+                self._train_batched(batch_rows, lr)
+            except cb.BatchedUnsupported:
+                slice_rows = sorted(slice_rows + batch_rows)
+        for r in slice_rows:
+            self._train_timesliced(r, local_steps, lr)
+
+    # -- batched fedsgd ------------------------------------------------------------
+    def stage_batches(self, rows: Optional[Sequence[int]] = None, num_batches: int = 1):
+        """Host->device copy of the next round's inputs from pinned memory (async)."""
+        rows = list(range(len(self.local_idx))) if rows is None else list(rows)
+        ids = [self.clients[self.local_idx[r]].id() for r in rows]
+        X, y = self.dataset.get_train_batches(ids, num_batches)
+        self.h2d_bytes = X.numel() * X.element_size() + y.numel() * y.element_size()
+        nb = self.device.type == "cuda"
+        return X.to(self.device, non_blocking=nb), y.to(self.device, non_blocking=nb)
+
+    def _train_batched(self, rows: List[int], lr: float) -> None:
+        model = self.server.get_model()
+        n = len(rows)
+        X, y = self.stage_batches(rows, 1)
+        X = X[:, 0]
+        y = y[:, 0]
+        B = X.shape[1]
+        clamp = torch.empty(n, device=self.device)
+        signs = []
+        for j, r in enumerate(rows):
+            c = self.clients[self.local_idx[r]]
+            clamp[j] = c.loss_clamp
+            if _overrides(c, "on_train_batch_begin"):
+                xj, yj = c.on_train_batch_begin(data=X[j], target=y[j])
+                if xj is not X[j]:
+                    X[j] = xj
+                y[j] = yj
+            if getattr(c, "grad_sign", 1.0) != 1.0:
+                signs.append((r, float(c.grad_sign)))
+        contiguous_rows = rows == list(range(rows[0], rows[0] + n))
+        out = self.U[rows[0]: rows[0] + n] if contiguous_rows else torch.empty(n, self.d, device=self.device)
+        sink = cb.GradSink(out, self.gflat.specs, n, alpha=-lr)
+        model.train()
+        with cb.client_batched(model, sink, n * B):
+            logits = model(X.reshape((n * B,) + tuple(X.shape[2:])))
+            loss, per_client = cb.batched_loss(logits, y.reshape(-1), n, clamp)
+            loss.backward()
+        missing = [s.name for s in self.gflat.specs if s.name not in sink.written]
+        for name in missing:       # parameters unused in the forward pass: zero update
+            sink.view(name).zero_()
+        if not contiguous_rows:
+            self.U[rows] = out
+        for r, sgn in signs:
+            self.U[r].mul_(sgn)
+        self.last_client_losses = per_client
+
+    # -- time-sliced (fedavg, custom clients) --------------------------------------------
+    def _lend(self, c: BladesClient, lr: float):
+        c.model = self.worker
+        if self.client_opt_spec in ("SGD", None, torch.optim.SGD):
+            c.optimizer = self.worker_opt
+        else:
+            c.optimizer = self.client_opt_spec(self.worker.parameters(), lr=lr)
+        c.set_lr(lr)
+
+    def _train_timesliced(self, r: int, local_steps: int, lr: float) -> None:
+        gi = self.local_idx[r]
+        c = self.clients[gi]
+        with torch.no_grad():
+            self.wflat.theta.copy_(self.gflat.theta)
+            for (_, bw), (_, bg) in zip(self.worker.named_buffers(), self.server.get_model().named_buffers()):
+                bw.copy_(bg)
+        self._lend(c, lr)
+        custom_begin = _overrides(c, "on_train_round_begin")
+        custom_end = _overrides(c, "on_train_round_end")
+        if custom_begin or custom_end:
+            c.on_train_round_begin()
+        else:
+            self.worker.train()
+        data = self.dataset.get_train_data(c.id(), local_steps)
+        c.local_training(data_batches=data)
+        if custom_end:
+            c.on_train_round_end()          # client computes/saves its own update (lands in U via bind_row)
+        else:
+            with torch.no_grad():
+                if not self.wflat.is_aliased():
+                    self.wflat.realias()
+                torch.sub(self.wflat.theta, self.gflat.theta, out=self.U[r])
+                c._state["saved_update"] = self.U[r]
+        c.model = None
+        c.optimizer = None
+
+    # ------------------------------------------------------------------ attack phase
+    def fusable_attack(self, callbacks: Sequence[Callable]) -> Optional[VirtualRows]:
+        """If every registered omniscient callback belongs to a stock ALIE/IPM client with
+        identical parameters, describe the attack as virtual rows."""
+        if not callbacks:
+            return None
+        owners = []
+        for fn in callbacks:
+            owner = getattr(fn, "__self__", None)
+            if not isinstance(owner, ByzantineClient):
+                return None
+            spec = owner.fused_spec()
+            stock = any(type(owner).omniscient_callback is getattr(k, "omniscient_callback")
+                        for k in _fusable_classes())
+            if spec is None or not stock:
+                return None
+            owners.append((owner, spec))
+        kinds = {(s["kind"], round(s["param"], 12)) for _, s in owners}
+        if len(kinds) != 1:
+            return None
+        idx_of = {id(c): i for i, c in enumerate(self.clients)}
+        replaced = sorted(idx_of[id(o)] for o, _ in owners if id(o) in idx_of)
+        if len(replaced) != len(owners):
+            return None
+        byz = [i for i, c in enumerate(self.clients) if c.is_byzantine()]
+        kind, param = owners[0][1]["kind"], owners[0][1]["param"]
+        return VirtualRows(kind, param, replaced, byz)
+
+    # ------------------------------------------------------------------ aggregation
+    def make_matrix(self, virtual: Optional[VirtualRows] = None) -> UpdateMatrix:
+        if self.symm is not None:
+            from ..parallel.sharded import ShardedMatrix
+            return ShardedMatrix(self.symm, virtual=virtual)
+        return LocalMatrix(self.U, virtual=virtual, use_kernels=self.use_kernels and self.U.is_cuda)
+
+    def gather_dense(self) -> torch.Tensor:
+        """Dense [N, d] on every rank (escape hatch for custom callbacks/aggregators)."""
+        if not self.world.distributed:
+            return self.U
+        import torch.distributed as dist
+        nmax = max(self.shard_sizes)
+        pad = torch.zeros(nmax, self.d, device=self.U.device)
+        pad[: self.U.shape[0]] = self.U
+        out = [torch.empty_like(pad) for _ in range(self.world.size)]
+        dist.all_gather(out, pad)
+        return torch.cat([o[:k] for o, k in zip(out, self.shard_sizes)], 0)

@@ -1,0 +1,233 @@
+"""Engine tests: client-batched fedsgd == time-sliced per-client training; API contract."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from blades_b200 import BladesClient, ByzantineClient, Simulator
+from blades_b200.datasets import synthetic_fldataset
+from blades_b200.engine import batched as cb
+from blades_b200.engine.flat import FlatParams
+from blades_b200.models import MLP, CCTNet, resnet18
+from blades_b200.models.cifar10.cctnets import cct_2_3x2_32
+
+
+def per_client_reference(model, X, y, lr, clamp=1e6):
+    """Plain autograd: one SGD step per client from the same weights -> delta rows."""
+    rows = []
+    for c in range(X.shape[0]):
+        m = copy.deepcopy(model)
+        m.train()
+        before = torch.cat([p.detach().reshape(-1) for p in m.parameters() if p.requires_grad])
+        opt = torch.optim.SGD(m.parameters(), lr=lr)
+        opt.zero_grad()
+        loss = torch.clamp(nn.functional.cross_entropy(m(X[c]), y[c]), 0, clamp)
+        loss.backward()
+        opt.step()
+        after = torch.cat([p.detach().reshape(-1) for p in m.parameters() if p.requires_grad])
+        rows.append(after - before)
+    return torch.stack(rows)
+
+
+def batched_rows(model, X, y, lr):
+    n, B = X.shape[:2]
+    flat = FlatParams(model, dtype=next(model.parameters()).dtype)
+    U = torch.zeros(n, flat.numel, dtype=flat.dtype)
+    sink = cb.GradSink(U, flat.specs, n, alpha=-lr)
+    model.train()
+    with cb.client_batched(model, sink, n * B):
+        logits = model(X.reshape((n * B,) + tuple(X.shape[2:])))
+        loss, _ = cb.batched_loss(logits, y.reshape(-1), n, torch.full((n,), 1e6, dtype=logits.dtype))
+        loss.backward()
+    assert sink.written == {s.name for s in flat.specs}
+    return U
+
+
+@pytest.mark.parametrize("name", ["mlp", "resnet18", "resnet18_gn", "cct"])
+def test_batched_equals_per_client(name):
+    torch.manual_seed(0)
+    if name == "mlp":
+        model, shape, ncls = MLP(), (28, 28), 10
+    elif name == "resnet18":
+        model, shape, ncls = resnet18(num_classes=10), (3, 32, 32), 10
+    elif name == "resnet18_gn":
+        model, shape, ncls = resnet18(num_classes=10, norm="group"), (3, 32, 32), 10
+    else:
+        model = cct_2_3x2_32(attention_dropout=0.0, stochastic_depth=0.0)
+        shape, ncls = (3, 32, 32), 10
+    n, B = 3, 4
+    model = model.double()          # exact comparison: fp32 BN over 4 samples is ill-conditioned
+    X = torch.randn(n, B, *shape, dtype=torch.float64)
+    y = torch.randint(0, ncls, (n, B))
+    ref = per_client_reference(model, X, y, 0.1)
+    got = batched_rows(copy.deepcopy(model), X, y, 0.1)
+    assert torch.allclose(got, ref, atol=1e-9, rtol=1e-7), float((got - ref).abs().max())
+    # forward swaps are undone
+    assert "forward" not in model.__dict__
+
+
+def test_unbatchable_model_detected():
+    class Odd(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = nn.Parameter(torch.randn(5, 5))
+
+        def forward(self, x):
+            return x @ self.w
+    assert not cb.is_batchable(Odd())
+    assert cb.is_batchable(MLP()) and cb.is_batchable(resnet18()) and cb.is_batchable(CCTNet())
+
+
+def _run(agg, attack=None, nbyz=0, agg_kws=None, attack_kws=None, rounds=2, local_steps=1, tmp="", n=6,
+         model=None, **kw):
+    ds = synthetic_fldataset(n, shape=(28, 28), num_classes=10, train_bs=8, train_per_client=32,
+                             test_per_client=16, seed=3)
+    sim = Simulator(ds, num_byzantine=nbyz, attack=attack, attack_kws=attack_kws, aggregator=agg,
+                    aggregator_kws=agg_kws, log_path=tmp, seed=1, progress=False, **kw)
+    torch.manual_seed(5)
+    m = model or MLP()
+    times = sim.run(m, global_rounds=rounds, local_steps=local_steps, server_lr=1.0, client_lr=0.1,
+                    validate_interval=rounds)
+    return sim, m, times
+
+
+def test_fedsgd_batched_matches_timesliced_end_to_end(tmp_log):
+    # same seed, same data streams: batched engine vs forced time-slicing (custom optimizer factory)
+    sim1, m1, t1 = _run("mean", tmp=tmp_log + "a")
+    ds = synthetic_fldataset(6, shape=(28, 28), num_classes=10, train_bs=8, train_per_client=32,
+                             test_per_client=16, seed=3)
+    sim2 = Simulator(ds, aggregator="mean", log_path=tmp_log + "b", seed=1, progress=False)
+    torch.manual_seed(5)
+    m2 = MLP()
+    sim2.run(m2, client_optimizer=lambda params, lr: torch.optim.SGD(params, lr=lr), global_rounds=2,
+             local_steps=1, server_lr=1.0, client_lr=0.1, validate_interval=2)
+    for p1, p2 in zip(m1.parameters(), m2.parameters()):
+        assert torch.allclose(p1, p2, atol=1e-5)
+    assert len(t1) == 2
+
+
+@pytest.mark.parametrize("agg,kws", [("mean", None), ("median", None), ("trimmedmean", {"nb": 1}),
+                                     ("krum", {"num_clients": 6, "num_byzantine": 1}), ("geomed", None),
+                                     ("autogm", None), ("centeredclipping", None), ("clustering", None),
+                                     ("clippedclustering", None), ("multikrum", {"num_byzantine": 1})])
+@pytest.mark.parametrize("attack", [None, "noise", "labelflipping", "signflipping", "alie", "ipm"])
+def test_all_attack_aggregator_pairs_run(agg, kws, attack, tmp_log):
+    akw = {"num_clients": 6, "num_byzantine": 1} if attack == "alie" else None
+    sim, m, _ = _run(agg, attack, 1 if attack else 0, kws, akw, rounds=1, tmp=tmp_log)
+    assert all(torch.isfinite(p).all() for p in m.parameters())
+
+
+def test_fused_attack_equals_callback_path(tmp_log):
+    out = []
+    for fuse in (True, False):
+        sim, m, _ = _run("trimmedmean", "alie", 2, {"nb": 2}, {"num_clients": 6, "num_byzantine": 2},
+                         rounds=2, tmp=tmp_log + str(fuse), fuse_attack=fuse)
+        out.append(torch.cat([p.detach().reshape(-1) for p in m.parameters()]))
+    assert torch.allclose(out[0], out[1], atol=1e-5)
+
+
+def test_fedavg_update_is_param_difference(tmp_log):
+    sim, m, _ = _run("mean", rounds=1, local_steps=3, tmp=tmp_log)
+    U = sim.engine.U
+    assert U.abs().sum() > 0
+    # server: theta_new = theta_old + server_lr * mean(U)   (server_lr = 1)
+    # reconstruct theta_old from any client row: after - before relation is internal; check shape/finite
+    assert U.shape == (6, 59850) and torch.isfinite(U).all()
+
+
+def test_server_step_semantics(tmp_log):
+    from blades_b200.server import BladesServer
+    m = MLP()
+    flat = FlatParams(m)
+    before = flat.theta.clone()
+    opt = torch.optim.SGD(m.parameters(), lr=0.5)
+    srv = BladesServer(opt, m, aggregator=None, flat=flat)
+    upd = torch.randn(flat.numel)
+    srv.apply_update(upd)
+    assert torch.allclose(flat.theta, before + 0.5 * upd)
+    # generic path (momentum) equals torch semantics with grad = -update
+    m2 = MLP()
+    f2 = FlatParams(m2)
+    b2 = f2.theta.clone()
+    opt2 = torch.optim.SGD(m2.parameters(), lr=0.5, momentum=0.9)
+    srv2 = BladesServer(opt2, m2, aggregator=None, flat=f2)
+    srv2.apply_update(upd)
+    srv2.apply_update(upd)
+    assert torch.allclose(f2.theta, b2 + 0.5 * upd + 0.5 * (1.9 * upd), atol=1e-5)
+
+
+def test_api_contract(tmp_log):
+    ds = synthetic_fldataset(5, shape=(28, 28), train_bs=8)
+    with pytest.raises(RuntimeError, match="Unknown keyword"):
+        Simulator(ds, log_path=tmp_log, bogus=1)
+    sim = Simulator(ds, num_byzantine=2, attack="ipm", aggregator="median", log_path=tmp_log, seed=1,
+                    progress=False)
+    cl = sim.get_clients()
+    assert [c.is_byzantine() for c in cl] == [True, True, False, False, False]
+    assert [c.id() for c in cl] == [0, 1, 2, 3, 4]
+    assert len(sim.omniscient_callbacks) == 2
+    sim.set_trusted_clients([3])
+    assert cl[3].is_trusted() and not cl[2].is_trusted()
+    import os
+    assert os.path.isfile(os.path.join(tmp_log, "stats")) and os.path.isfile(os.path.join(tmp_log, "debug"))
+
+
+def test_custom_attacker_and_aggregator(tmp_log):
+    calls = {"cb": 0, "train": 0}
+
+    class Mal(ByzantineClient):
+        def local_training(self, data_batches):
+            calls["train"] += 1
+            super().local_training(data_batches)
+
+        def omniscient_callback(self, simulator):
+            calls["cb"] += 1
+            honest = [c.get_update() for c in simulator.get_clients() if not c.is_byzantine()]
+            self.save_update(-10 * torch.stack(honest).mean(0))
+
+    def my_agg(clients):
+        return torch.stack([c.get_update() for c in clients]).mean(0)
+
+    ds = synthetic_fldataset(5, shape=(28, 28), train_bs=8)
+    sim = Simulator(ds, aggregator=my_agg, log_path=tmp_log, seed=1, progress=False)
+    sim.register_attackers([Mal(), Mal()])
+    m = MLP()
+    sim.run(m, global_rounds=2, local_steps=2, validate_interval=1)
+    assert calls == {"cb": 4, "train": 4}
+    cl = sim.get_clients()
+    assert cl[0].is_byzantine() and cl[1].is_byzantine() and not cl[2].is_byzantine()
+    honest_mean = torch.stack([c.get_update() for c in cl[2:]]).mean(0)
+    assert torch.allclose(cl[0].get_update(), -10 * honest_mean, atol=1e-6)
+
+
+def test_loss_decreases_and_checkpoint_resume(tmp_log, tmp_path):
+    ds_args = dict(shape=(28, 28), num_classes=10, train_bs=16, train_per_client=64, test_per_client=32, seed=3, separation=2.0)
+    ck = str(tmp_path / "ck.pt")
+
+    def make():
+        ds = synthetic_fldataset(4, **ds_args)
+        return Simulator(ds, aggregator="centeredclipping", log_path=tmp_log, seed=1, progress=False)
+
+    sim = make()
+    torch.manual_seed(0)
+    m = MLP()
+    sim.run(m, global_rounds=6, local_steps=2, server_lr=1.0, client_lr=0.1, validate_interval=1,
+            checkpoint_path=ck, checkpoint_interval=3)
+    recs = [eval(l) for l in open(tmp_log + "/stats") if "'test'" in l]
+    assert recs[-1]["Loss"] < recs[0]["Loss"]
+    final = torch.cat([p.detach().reshape(-1) for p in m.parameters()]).clone()
+    # checkpoint written at round 6 overwrote round 3; take a fresh run to round 3 then resume
+    sim_a = make()
+    torch.manual_seed(0)
+    ma = MLP()
+    sim_a.run(ma, global_rounds=3, local_steps=2, server_lr=1.0, client_lr=0.1, validate_interval=1,
+              checkpoint_path=ck, checkpoint_interval=3)
+    sim_b = make()
+    mb = MLP()
+    sim_b.run(mb, global_rounds=6, local_steps=2, server_lr=1.0, client_lr=0.1, validate_interval=1, resume=ck)
+    resumed = torch.cat([p.detach().reshape(-1) for p in mb.parameters()])
+    assert torch.allclose(resumed, final, atol=1e-6)
+    sd = torch.load(ck, weights_only=False)
+    MLP().load_state_dict(sd["model"])
