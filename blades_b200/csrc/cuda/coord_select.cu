@@ -1,0 +1,212 @@
+// Coordinate-wise robust selection over the client dimension -- K3/K4 (+K7 prologue, K8 epilogue)
+// of SURVEY 2.7: trimmed mean (reference trimmedmean.py:38-41: two strided topk + 3 temporaries)
+// and median (reference median.py:23-24: two kthvalue passes) in ONE streaming pass.
+//
+// One thread owns one coordinate: it loads that coordinate from every client row (rows may live
+// on peer GPUs -- plain global loads on NVLink-mapped pointers, coalesced 128 B per warp per row),
+// sorts the <=128 values in registers with a static pruned Batcher network, and reduces the ranks
+// it needs.  ALIE / IPM attackers are *virtual rows*: their common value (mean - z*std, or
+// -eps*mean, over the honest rows) is computed from the same registers and merged analytically
+// with multiplicity f -- f identical malicious rows are never stored or sorted.
+// The result is written to every replica and theta += lr*agg is applied in the same kernel.
+#include "common.cuh"
+
+#define CE(a, b) { float lo_ = fminf(v[a], v[b]); v[b] = fmaxf(v[a], v[b]); v[a] = lo_; }
+#include "gen/sortnet_gen.cuh"
+#undef CE
+
+struct SelectParams {
+    const float* rows[128];   // real rows: honest first (stat rows), then other real rows
+    int n_real;               // number of real rows (<= NP)
+    int n_stat;               // first n_stat rows enter the attack statistics
+    int n_virtual;            // multiplicity f of the virtual row
+    int virt_kind;            // 0 none, 1 ALIE (mean - p*std_unbiased), 2 IPM (-p*mean)
+    float virt_param;
+    int mode;                 // 0 trimmed mean, 1 median
+    int trim_b;
+    long long c0, c1;         // coordinate range owned by this launch
+    BlEpilogue ep;
+};
+
+template <int NP>
+__global__ void __launch_bounds__(128)
+coord_select_kernel(const __grid_constant__ SelectParams p) {
+    const long long c = p.c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.c1) return;
+    float v[NP];
+    const int n = p.n_real;
+#pragma unroll
+    for (int i = 0; i < NP; ++i)
+        v[i] = (i < n) ? bl_sanitize(bl_ldg_stream(p.rows[i] + c)) : INFINITY;
+
+    // ---- attack prologue (K7): statistics of the honest rows, still in load order
+    float m = 0.f;
+    const int f = p.n_virtual;
+    if (f > 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) s += (i < p.n_stat) ? v[i] : 0.f;
+        const float mu = s / (float)p.n_stat;
+        if (p.virt_kind == 1) {
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) { float d = v[i] - mu; q += (i < p.n_stat) ? d * d : 0.f; }
+            m = mu - p.virt_param * sqrtf(q / (float)(p.n_stat - 1));
+        } else {
+            m = -p.virt_param * mu;
+        }
+    }
+
+    SortNet<NP>::run(v);
+
+    // ---- merge the virtual value with multiplicity f: r = #real values below m
+    const int N = n + f;
+    int r = 0;
+    if (f > 0) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) r += (v[i] < m) ? 1 : 0;
+    }
+    float agg;
+    if (p.mode == 0) {
+        const int lo = p.trim_b, hi = N - p.trim_b;          // keep merged ranks [lo, hi)
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            const int pos = i + ((i >= r) ? f : 0);
+            s += (pos >= lo && pos < hi) ? v[i] : 0.f;
+        }
+        if (f > 0) {
+            const int a = max(r, lo), b = min(r + f, hi);
+            if (b > a) s += m * (float)(b - a);
+        }
+        agg = s / (float)(hi - lo);
+    } else {
+        const int k0 = (N - 1) >> 1, k1 = N >> 1;
+        float a0 = (f > 0 && k0 >= r && k0 < r + f) ? m : 0.f;
+        float a1 = (f > 0 && k1 >= r && k1 < r + f) ? m : 0.f;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            const int pos = i + ((i >= r) ? f : 0);
+            a0 += (pos == k0) ? v[i] : 0.f;
+            a1 += (pos == k1) ? v[i] : 0.f;
+        }
+        agg = 0.5f * (a0 + a1);
+    }
+    bl_epilogue_store(p.ep, c, agg);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Large-N fallback (128 < N <= 512): a block sorts a [NP x 32-coordinate] tile in shared memory
+// with a bitonic network (one __syncthreads per stage).  Virtual rows are materialised into the
+// tile (value computed per coordinate first).
+struct SelectLargeParams {
+    const float* rows[BL_MAX_ROWS];
+    int n_real, n_stat, n_virtual, virt_kind;
+    float virt_param;
+    int mode, trim_b;
+    long long c0, c1;
+    BlEpilogue ep;
+};
+
+template <int NP>
+__global__ void __launch_bounds__(256)
+coord_select_large_kernel(const __grid_constant__ SelectLargeParams p) {
+    extern __shared__ float tile[];                 // [NP][33]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const long long c = p.c0 + (long long)blockIdx.x * 32 + lane;
+    const bool live = c < p.c1;
+    const int n = p.n_real, f = p.n_virtual, N = n + f;
+    for (int i = wid; i < NP; i += nw) {
+        float x = INFINITY;
+        if (i < n && live) x = bl_sanitize(bl_ldg_stream(p.rows[i] + c));
+        tile[i * 33 + lane] = x;
+    }
+    __syncthreads();
+    if (f > 0) {
+        // per-coordinate statistics by warp 0 (n_stat <= 512 values, sequential per lane)
+        if (wid == 0) {
+            float s = 0.f;
+            for (int i = 0; i < p.n_stat; ++i) s += tile[i * 33 + lane];
+            const float mu = s / (float)p.n_stat;
+            float m;
+            if (p.virt_kind == 1) {
+                float q = 0.f;
+                for (int i = 0; i < p.n_stat; ++i) { float d = tile[i * 33 + lane] - mu; q += d * d; }
+                m = mu - p.virt_param * sqrtf(q / (float)(p.n_stat - 1));
+            } else m = -p.virt_param * mu;
+            for (int i = n; i < N; ++i) tile[i * 33 + lane] = live ? m : INFINITY;
+        }
+        __syncthreads();
+    }
+    for (int k = 2; k <= NP; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = wid; t < NP / 2; t += nw) {
+                const int i = 2 * t - (t & (j - 1));      // index with bit j clear
+                const int ixj = i + j;
+                const bool up = ((i & k) == 0);
+                float a = tile[i * 33 + lane], b = tile[ixj * 33 + lane];
+                const float lo = fminf(a, b), hi = fmaxf(a, b);
+                tile[i * 33 + lane] = up ? lo : hi;
+                tile[ixj * 33 + lane] = up ? hi : lo;
+            }
+            __syncthreads();
+        }
+    if (wid == 0 && live) {
+        float agg;
+        if (p.mode == 0) {
+            float s = 0.f;
+            for (int i = p.trim_b; i < N - p.trim_b; ++i) s += tile[i * 33 + lane];
+            agg = s / (float)(N - 2 * p.trim_b);
+        } else {
+            agg = 0.5f * (tile[((N - 1) >> 1) * 33 + lane] + tile[(N >> 1) * 33 + lane]);
+        }
+        bl_epilogue_store(p.ep, c, agg);
+    }
+}
+
+template <int NP>
+static cudaError_t launch_small(const SelectParams& p, cudaStream_t st) {
+    const long long cols = p.c1 - p.c0;
+    if (cols <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((cols + 127) / 128);
+    coord_select_kernel<NP><<<grid, 128, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+extern "C" int bl_coord_select(const SelectParams* p, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = p->n_real;
+    if (n < 1 || n > 128) return -1;
+    switch ((n + 7) / 8) {
+#define CASE(K) case K: return (int)launch_small<8 * K>(*p, st);
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+        CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16)
+#undef CASE
+    }
+    return -1;
+}
+
+extern "C" int bl_coord_select_large(const SelectLargeParams* p, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = p->n_real + p->n_virtual;
+    if (N < 1 || N > BL_MAX_ROWS) return -1;
+    const long long cols = p->c1 - p->c0;
+    if (cols <= 0) return 0;
+    const unsigned grid = (unsigned)((cols + 31) / 32);
+    int np = 64;
+    while (np < N) np <<= 1;
+    const size_t smem = (size_t)np * 33 * sizeof(float);
+    cudaError_t e;
+#define LAUNCH(NPV)                                                                              \
+    e = cudaFuncSetAttribute(coord_select_large_kernel<NPV>,                                       \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+    if (e != cudaSuccess) return (int)e;                                                           \
+    coord_select_large_kernel<NPV><<<grid, 256, smem, st>>>(*p);
+    if (np == 64) { LAUNCH(64) } else if (np == 128) { LAUNCH(128) }
+    else if (np == 256) { LAUNCH(256) } else { LAUNCH(512) }
+#undef LAUNCH
+    return (int)cudaGetLastError();
+}
+
+extern "C" int bl_sizeof_select_params() { return (int)sizeof(SelectParams); }
+extern "C" int bl_sizeof_select_large_params() { return (int)sizeof(SelectLargeParams); }

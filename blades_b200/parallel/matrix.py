@@ -125,8 +125,15 @@ class LocalMatrix(UpdateMatrix):
         """Write the virtual rows into ``data`` (what the reference's callbacks do)."""
         v = self.virtual
         if v is not None and v.count:
-            val = v.value(self._honest())
-            self.data[list(v.replaced)] = val
+            if self.use_kernels:
+                from ..ops import attack as _a, select as _s
+                byz = set(v.byzantine)
+                honest = [i for i in range(self.n_rows) if i not in byz]
+                _a.attack_rows(_s.row_pointers(self.data, honest), _s.row_pointers(self.data, list(v.replaced)),
+                               v.kind, v.param, 0, self.n_cols, self.data.device)
+            else:
+                val = v.value(self._honest())
+                self.data[list(v.replaced)] = val
             self.virtual = None
         return self.data
 
