@@ -25,6 +25,9 @@ class _BaseAggregator:
     supports_virtual_rows = True
     #: reference-quirk compatibility switch; default = reference behaviour
     compat = True
+    #: the returned vector is exactly the output of the last matrix primitive, so the server step
+    #: ``theta += lr * agg`` may be fused into that kernel's epilogue
+    fusable_final = True
 
     def __init__(self, *args, **kwargs):
         pass

@@ -18,6 +18,7 @@ def _get_vectorized_parameters(optimizer) -> torch.Tensor:
 
 
 class ByzantineSGD(_BaseAggregator):
+    fusable_final = False
     def __init__(self, m, th_A, th_B, th_V, optimizer):
         super().__init__()
         self.m = m

@@ -47,10 +47,9 @@ class Centeredclipping(_BaseAggregator):
             m = self.momentum.to(matrix.device)
             G_aug = matrix.gram(extra=m)
             c = gops.centered_clip_coeffs(G_aug, self.tau, self.n_iter)
-            new_m = matrix.combine(c[:n])
-            new_m = new_m + float(c[n]) * m.to(new_m.dtype)
-        self.momentum = new_m
-        return new_m.detach().clone()
+            new_m = matrix.combine(c[:n], extra=m.to(torch.float32) if m.is_cuda else m, extra_weight=float(c[n]))
+        self.momentum = new_m.detach().clone()      # the returned vector may be a reused device buffer
+        return new_m
 
     def state_dict(self):
         return {"momentum": None if self.momentum is None else self.momentum.detach().cpu()}

@@ -1,0 +1,85 @@
+"""NVLink-addressable symmetric memory for the update rows, the aggregate and the parameter
+replica of every trainer shard.
+
+One symmetric allocation per rank (``torch.distributed._symmetric_memory``: CUDA VMM + IPC handle
+exchange; NVLS multicast object when the fabric supports it), laid out identically everywhere:
+
+    [ U_g : nmax rows x ld floats ][ agg : ld ][ theta : ld ]
+
+so every kernel can address any peer's rows/agg/theta as ``peer_base[r] + same offset``.  ``ld`` is
+``d`` rounded up to 64 floats: rows are 256 B aligned for 16 B vector loads and TMA.
+
+Synchronisation: ``barrier()`` is the symmetric-memory device barrier (signal-pad flags over NVLink,
+enqueued on the current stream -- no host round trip).  Protocol per round:
+    train (writes own rows) -> barrier -> fused pull-aggregate kernels (read all rows, write
+    agg/theta shards to all peers) -> barrier -> next round.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+import torch.distributed as dist
+
+__all__ = ["SymmetricUpdates", "round_up"]
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class SymmetricUpdates:
+    def __init__(self, world, shard_sizes: Sequence[int], d: int):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.world = world
+        self.shard_sizes = list(shard_sizes)
+        self.d = d
+        self.ld = round_up(d, 64)
+        self.nmax = max(self.shard_sizes)
+        self.n_local = self.shard_sizes[world.rank]
+        self.n_total = sum(self.shard_sizes)
+        total = self.nmax * self.ld + 2 * self.ld
+        self.buf = symm_mem.empty((total,), dtype=torch.float32, device=world.device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, dist.group.WORLD)
+        self.base_ptrs: List[int] = [int(p) for p in self.handle.buffer_ptrs]
+        self.off_agg = self.nmax * self.ld
+        self.off_theta = self.off_agg + self.ld
+        self.local_full = self.buf[: self.nmax * self.ld].view(self.nmax, self.ld)
+        self.local = self.local_full[: self.n_local, :d]
+        self.agg = self.buf[self.off_agg: self.off_agg + d]
+        self.theta = self.buf[self.off_theta: self.off_theta + d]
+        self.multicast_ptr = int(self.handle.multicast_ptr) if getattr(self.handle, "multicast_ptr", 0) else 0
+        # global row -> (rank, local row)
+        self.row_owner = []
+        for r, k in enumerate(self.shard_sizes):
+            self.row_owner += [(r, i) for i in range(k)]
+        # coordinate shards: boundaries aligned to 128 floats
+        G = world.size
+        cuts = [min(d, round_up(d * r // G, 128)) for r in range(G)] + [d]
+        self.col_ranges = [(cuts[r], cuts[r + 1]) for r in range(G)]
+
+    # ------------------------------------------------------------------ addressing
+    def row_ptr(self, global_row: int) -> int:
+        r, i = self.row_owner[global_row]
+        return self.base_ptrs[r] + i * self.ld * 4
+
+    def row_ptrs(self, rows: Sequence[int]) -> List[int]:
+        return [self.row_ptr(g) for g in rows]
+
+    def agg_ptrs(self) -> List[int]:
+        return [b + self.off_agg * 4 for b in self.base_ptrs]
+
+    def theta_ptrs(self) -> List[int]:
+        return [b + self.off_theta * 4 for b in self.base_ptrs]
+
+    def block_descs(self):
+        """(base_ptr, ld, rows) of every rank's row block, in global row order."""
+        return [(self.base_ptrs[r], self.ld, k) for r, k in enumerate(self.shard_sizes) if k > 0]
+
+    @property
+    def my_cols(self):
+        return self.col_ranges[self.world.rank]
+
+    def barrier(self) -> None:
+        self.handle.barrier(channel=0)

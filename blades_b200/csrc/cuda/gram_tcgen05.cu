@@ -1,0 +1,281 @@
+// Split-K Gram matrix  G = U U^T  on the 5th-gen tensor cores -- K5 of SURVEY 2.7.
+// Replaces the reference's O(N^2) Python loops of (v1 - v2).norm() / scipy cosine over CPU vectors
+// (krum.py:85-90, clustering.py:28-33, clippedclustering.py:52-57, geomed.py:62,74): every pairwise
+// distance / cosine / norm is derived from G on the host (aggregators/_gramops.py).
+//
+// Shape of the problem: M = N = #clients (<= 512), K = d = 11-24 M coordinates -> memory bound
+// (each element of U must stream from HBM / NVLink exactly once).  Design:
+//   * persistent split-K: CTA (ks, grp) owns a contiguous range of 32-float K chunks and
+//     `mb_per_cta` 128-row M blocks; its fp32 accumulators (128 x NP per M block) live in TMEM for
+//     the whole kernel and are flushed once with red.global.add at the end.
+//   * operands: one smem tile [tile_rows x 128 B] per stage holds the K chunk of ALL rows (A blocks
+//     are sub-ranges of the B tile, so every byte is loaded once per CTA).  Row blocks may live on
+//     different GPUs: one TMA descriptor per block (peer memory is TMA-addressable through the
+//     NVLink mapping); SWIZZLE_128B, K-major; out-of-range rows/columns are zero-filled by TMA.
+//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread issues
+//     tcgen05.mma.kind::tf32), warps 2-5 = converter + epilogue.  The converter sanitises NaN/inf
+//     (nan_to_num) and, for 3xTF32, splits x = hi + lo (hi = tf32-truncated) into two smem tiles so
+//     that  hi*hi + hi*lo + lo*hi  recovers ~fp32 accuracy (distances suffer cancellation).
+//   * pipeline: full[s] (TMA -> converter), ready[s] (converter -> MMA), empty[s] (tcgen05.commit ->
+//     TMA), done (last commit -> epilogue).
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <cstring>
+
+#define GRAM_MAX_BLOCKS 9          // 8 peers + 1 extra row block
+#define GRAM_CHUNK 32              // floats per K chunk = 128 B = one swizzle row
+
+struct GramParams {
+    CUtensorMap maps[GRAM_MAX_BLOCKS];
+    int n_blocks;
+    int blk_rows_pad[GRAM_MAX_BLOCKS];   // TMA box rows (multiple of 8)
+    int blk_smem_row[GRAM_MAX_BLOCKS];   // first row of the block inside the stage tile
+    int rows_covered;                    // sum of blk_rows_pad
+    int tile_rows;                       // n_mblk * 128
+    int np_n;                            // MMA N extent (multiple of 16, >= rows_covered, <= 512)
+    int n_mblk;
+    int mb_per_cta;
+    int stages;
+    int split3;                          // 1 = 3xTF32
+    long long chunk0, chunk1;            // K chunk range of this launch
+    float* gram;                         // [tile_rows][ld_gram] fp32, accumulated with red.add
+    int ld_gram;
+};
+
+namespace {
+
+constexpr int kThreads = 192;            // 6 warps
+
+__global__ void __launch_bounds__(kThreads, 1)
+gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [stages][hi tile][lo tile?] then barriers
+    const uint32_t tile_bytes = (uint32_t)p.tile_rows * 128u;
+    const uint32_t stage_bytes = tile_bytes * (p.split3 ? 2u : 1u);
+    uint8_t* tiles = smem_raw;                       // dynamic smem base is 1024-aligned (checked on host)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)p.stages * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* ready = bars + p.stages;
+    uint64_t* empty = bars + 2 * p.stages;
+    uint64_t* done = bars + 3 * p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // ---- work assignment
+    const int ksplits = gridDim.x;
+    const long long nchunks = p.chunk1 - p.chunk0;
+    const long long per = (nchunks + ksplits - 1) / ksplits;
+    const long long kc0 = p.chunk0 + per * blockIdx.x;
+    const long long kc1 = min(p.chunk1, kc0 + per);
+    const int mb0 = blockIdx.y * p.mb_per_cta;
+    const int nmb = min(p.mb_per_cta, p.n_mblk - mb0);
+    const int iters = (int)max(0LL, kc1 - kc0);
+    const uint32_t tmem_cols_needed = (uint32_t)(p.mb_per_cta * p.np_n);
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < tmem_cols_needed) tmem_cols <<= 1;
+
+    // ---- one-time setup
+    if (warp == 0 && lane == 0) {
+        for (int b = 0; b < p.n_blocks; ++b) bl::tma_prefetch_desc(&p.maps[b]);
+        for (int s = 0; s < p.stages; ++s) {
+            bl::mbar_init(&full[s], 1);
+            bl::mbar_init(&ready[s], 4);     // one arrive per converter warp
+            bl::mbar_init(&empty[s], 1);
+        }
+        bl::mbar_init(done, 1);
+        bl::fence_barrier_init();
+    }
+    if (warp == 1) bl::tmem_alloc_dyn(tmem_slot, tmem_cols);
+    // rows of the tile that no TMA box covers must read as zero (hi and lo tiles, every stage)
+    if (p.rows_covered < p.tile_rows) {
+        const uint32_t beg = (uint32_t)p.rows_covered * 128u;
+        for (int s = 0; s < p.stages; ++s)
+            for (int t = 0; t < (p.split3 ? 2 : 1); ++t) {
+                uint8_t* base = tiles + (size_t)s * stage_bytes + (size_t)t * tile_bytes;
+                for (uint32_t off = beg + threadIdx.x * 16u; off < tile_bytes; off += kThreads * 16u)
+                    *reinterpret_cast<float4*>(base + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        bl::fence_proxy_async_smem();
+    }
+    bl::tc_fence_before();
+    __syncthreads();
+    bl::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (iters > 0) {
+        if (warp == 0) {
+            // ================= TMA producer =================
+            if (lane == 0) {
+                const uint32_t tx = (uint32_t)p.rows_covered * 128u;
+                for (int it = 0; it < iters; ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    bl::mbar_wait(&empty[s], ph ^ 1u);
+                    bl::mbar_arrive_expect_tx(&full[s], tx);
+                    uint8_t* dst = tiles + (size_t)s * stage_bytes;
+                    const int c0 = (int)((kc0 + it) * GRAM_CHUNK);
+                    for (int b = 0; b < p.n_blocks; ++b)
+                        bl::tma_load_2d(dst + (size_t)p.blk_smem_row[b] * 128u, &p.maps[b], &full[s], c0, 0);
+                }
+            }
+        } else if (warp == 1) {
+            // ================= MMA issuer =================
+            const int n_halves = (p.np_n + 255) / 256;
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                bl::mbar_wait(&ready[s], ph);
+                bl::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t hi = bl::smem_u32(tiles + (size_t)s * stage_bytes);
+                    const uint32_t lo = hi + tile_bytes;
+                    for (int m = 0; m < nmb; ++m) {
+                        const uint32_t a_off = (uint32_t)(mb0 + m) * 128u * 128u;
+                        for (int h = 0; h < n_halves; ++h) {
+                            const int ncols = min(256, p.np_n - h * 256);
+                            const uint32_t idesc = bl::umma_idesc_tf32(128, (uint32_t)ncols, 0, 0);
+                            const uint32_t b_off = (uint32_t)h * 256u * 128u;
+                            const uint32_t d_tmem = tmem_base + (uint32_t)(m * p.np_n + h * 256);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {          // 4 x (K = 8 tf32 = 32 B) per 128 B row
+                                const uint32_t koff = (uint32_t)k * 32u;
+                                const uint64_t a_hi = bl::umma_smem_desc(hi + a_off + koff, 16, 1024);
+                                const uint64_t b_hi = bl::umma_smem_desc(hi + b_off + koff, 16, 1024);
+                                bl::umma_tf32(d_tmem, a_hi, b_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                                if (p.split3) {
+                                    const uint64_t a_lo = bl::umma_smem_desc(lo + a_off + koff, 16, 1024);
+                                    const uint64_t b_lo = bl::umma_smem_desc(lo + b_off + koff, 16, 1024);
+                                    bl::umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+                                    bl::umma_tf32(d_tmem, a_lo, b_hi, idesc, 1u);
+                                }
+                            }
+                        }
+                    }
+                    bl::umma_commit(&empty[s]);                    // smem slot reusable when MMAs retire
+                    if (it == iters - 1) bl::umma_commit(done);    // accumulators final
+                }
+                __syncwarp();
+            }
+        } else {
+            // ================= converter (warps 2..5) =================
+            const int ct = threadIdx.x - 64;                       // 0..127
+            const uint32_t n16 = (uint32_t)p.rows_covered * 8u;    // 16 B granules in the covered tile
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                bl::mbar_wait(&full[s], ph);
+                uint8_t* hi = tiles + (size_t)s * stage_bytes;
+                uint8_t* lo = hi + tile_bytes;
+                for (uint32_t g = ct; g < n16; g += 128) {
+                    float4 x = *reinterpret_cast<float4*>(hi + g * 16u);
+                    x.x = bl_sanitize(x.x); x.y = bl_sanitize(x.y); x.z = bl_sanitize(x.z); x.w = bl_sanitize(x.w);
+                    float4 h;
+                    h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                    h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                    h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                    h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                    *reinterpret_cast<float4*>(hi + g * 16u) = h;
+                    if (p.split3)
+                        *reinterpret_cast<float4*>(lo + g * 16u) =
+                            make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+                }
+                bl::fence_proxy_async_smem();                      // generic writes -> visible to UMMA
+                __syncwarp();
+                if (lane == 0) bl::mbar_arrive(&ready[s]);
+            }
+        }
+
+        // ================= epilogue (warps 2..5): TMEM -> red.global.add =================
+        if (warp >= 2) {
+            bl::mbar_wait(done, 0);
+            bl::tc_fence_after();
+            const int q = warp & 3;                                // TMEM lane quarter of this warp
+            for (int m = 0; m < nmb; ++m) {
+                const int row = (mb0 + m) * 128 + q * 32 + lane;
+                for (int c = 0; c < p.np_n; c += 32) {
+                    float v[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * p.np_n + c);
+                    bl::tmem_ld_32x32(taddr, v);
+                    if (row < p.rows_covered) {
+                        float* dst = p.gram + (size_t)row * p.ld_gram + c;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (c + j < p.rows_covered) atomicAdd(dst + j, v[j]);
+                    }
+                }
+            }
+        }
+    }
+    bl::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) bl::tmem_dealloc(tmem_base, tmem_cols);
+}
+
+}  // namespace
+
+// Host launcher.  blocks: base pointers of row blocks (each [rows_b x d], row stride ld_b floats).
+struct GramBlockDesc {
+    const float* base;
+    long long ld;        // row stride in floats (multiple of 4)
+    int rows;
+};
+
+extern "C" int bl_gram_tcgen05(const GramBlockDesc* blocks, int n_blocks, long long d, long long col0,
+                               long long col1, float* gram, int ld_gram, int split3, int num_sms,
+                               void* stream) {
+    if (n_blocks < 1 || n_blocks > GRAM_MAX_BLOCKS) return -1;
+    if (col0 % GRAM_CHUNK != 0) return -2;
+    GramParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_blocks = n_blocks;
+    int row = 0;
+    for (int b = 0; b < n_blocks; ++b) {
+        const int pad = (blocks[b].rows + 7) / 8 * 8;
+        if (pad > 256) return -3;                      // TMA box limit; callers split larger blocks
+        if (blocks[b].ld % 4 != 0 || ((uintptr_t)blocks[b].base) % 16 != 0) return -4;
+        p.blk_rows_pad[b] = pad;
+        p.blk_smem_row[b] = row;
+        row += pad;
+        uint64_t dims[2] = {(uint64_t)d, (uint64_t)blocks[b].rows};
+        uint64_t strides[1] = {(uint64_t)blocks[b].ld * 4};
+        uint32_t box[2] = {GRAM_CHUNK, (uint32_t)pad};
+        int r = bl::make_tmap_f32(&p.maps[b], blocks[b].base, 2, dims, strides, box);
+        if (r != 0) return 1000 + r;
+    }
+    p.rows_covered = row;
+    if (row > 512) return -5;
+    p.n_mblk = (row + 127) / 128;
+    p.tile_rows = p.n_mblk * 128;
+    p.np_n = (row + 15) / 16 * 16;
+    if (p.np_n < 16) p.np_n = 16;
+    // TMEM budget: mb_per_cta * np_n <= 512 columns; epilogue reads 32-column groups
+    p.np_n = (p.np_n + 31) / 32 * 32;
+    p.mb_per_cta = 512 / p.np_n;
+    if (p.mb_per_cta < 1) return -6;
+    if (p.mb_per_cta > p.n_mblk) p.mb_per_cta = p.n_mblk;
+    const int groups = (p.n_mblk + p.mb_per_cta - 1) / p.mb_per_cta;
+    p.split3 = split3 ? 1 : 0;
+    const size_t stage_bytes = (size_t)p.tile_rows * 128 * (p.split3 ? 2 : 1);
+    const size_t budget = 227 * 1024 - 1024 - 256;
+    int stages = (int)(budget / stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages < 2) return -7;
+    p.stages = stages;
+    p.chunk0 = col0 / GRAM_CHUNK;
+    p.chunk1 = (col1 + GRAM_CHUNK - 1) / GRAM_CHUNK;
+    p.gram = gram;
+    p.ld_gram = ld_gram;
+    const long long nchunks = p.chunk1 - p.chunk0;
+    if (nchunks <= 0) return 0;
+    int ksplits = (num_sms > 0 ? num_sms : 148) / groups;
+    if (ksplits < 1) ksplits = 1;
+    if ((long long)ksplits > nchunks) ksplits = (int)nchunks;
+    const size_t smem = (size_t)stages * stage_bytes + (3 * stages + 2) * sizeof(uint64_t) + 16;
+    cudaError_t e = cudaFuncSetAttribute(gram_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid(ksplits, groups);
+    gram_tcgen05_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,211 @@
+// Grouped (per-client) weight-gradient GEMM with the client-update epilogue -- K9 of SURVEY 2.7.
+//
+//     out[c][m][n] = alpha * sum_t  A[c*T + t][m] * B[c*T + t][n]        c = client, t = its T rows
+//
+// A = output-gradients [n_clients*T, M], B = layer inputs (or im2col rows) [n_clients*T, N], both
+// row-major, i.e. "MN-major" UMMA operands: no transposes are materialised.  `out` is a strided window
+// into the shard's update matrix U_g (batch stride = d floats), so the GEMM epilogue IS the client's
+// SGD step + update diff + nan_to_num + save_update of the reference (client.py:127-131,178-198):
+// alpha = -lr.  The problem is output-bound (K = T is 32..8192 while each client writes M*N floats),
+// so the kernel is organised around streaming 128x256 fp32 tiles out of TMEM at HBM write speed:
+//   warp 0   TMA producer: per stage 4 (A) + BN/32 (B) boxes of [KT rows x 128 B], SWIZZLE_128B
+//   warp 1   MMA issuer: tcgen05.mma.kind::tf32, M=128, N=BN, one K=8 atom per instruction,
+//            accumulators double-buffered in TMEM (2 x 256 columns)
+//   warps 2-5 epilogue: tcgen05.ld -> scale/sanitise -> 128 B-per-thread global stores
+// Persistent CTAs walk (client, m-tile, n-tile) tiles round-robin; smem and TMEM pipelines run
+// across tile boundaries so the next tile's loads/MMAs overlap the current tile's stores.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <cstring>
+
+struct WgradParams {
+    CUtensorMap map_a;       // 2D: (M, n_clients*T), box (32, KT)
+    CUtensorMap map_b;       // 2D: (N, n_clients*T), box (32, KT)
+    int n_clients, T, M, N;
+    int KT;                  // rows per stage (8/16/32, divides T)
+    int BN;                  // tile N (multiple of 32, <= 256)
+    int m_tiles, n_tiles;
+    int stages;
+    float alpha;
+    float* out;              // out[c*batch_stride + m*N + n]
+    long long batch_stride;
+    int vec_ok;              // 16 B aligned stores possible
+};
+
+namespace {
+constexpr int kWThreads = 192;
+
+__global__ void __launch_bounds__(kWThreads, 1)
+wgrad_tcgen05_kernel(const __grid_constant__ WgradParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t box_bytes = (uint32_t)p.KT * 128u;
+    const uint32_t a_bytes = 4u * box_bytes;
+    const uint32_t nb_blocks = (uint32_t)p.BN / 32u;
+    const uint32_t stage_bytes = a_bytes + nb_blocks * box_bytes;
+    uint8_t* tiles = smem_raw;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)p.stages * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + p.stages;
+    uint64_t* tfull = bars + 2 * p.stages;        // [2] accumulator ready
+    uint64_t* tempty = bars + 2 * p.stages + 2;   // [2] accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long total_tiles = (long long)p.n_clients * p.m_tiles * p.n_tiles;
+    const int ksteps = p.T / p.KT;
+
+    if (warp == 0 && lane == 0) {
+        bl::tma_prefetch_desc(&p.map_a);
+        bl::tma_prefetch_desc(&p.map_b);
+        for (int s = 0; s < p.stages; ++s) { bl::mbar_init(&full[s], 1); bl::mbar_init(&empty[s], 1); }
+        for (int i = 0; i < 2; ++i) { bl::mbar_init(&tfull[i], 1); bl::mbar_init(&tempty[i], 4); }
+        bl::fence_barrier_init();
+    }
+    if (warp == 1) bl::tmem_alloc<512>(tmem_slot);
+    bl::tc_fence_before();
+    __syncthreads();
+    bl::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = (int)(tile % p.n_tiles);
+                const int mt = (int)((tile / p.n_tiles) % p.m_tiles);
+                const int c = (int)(tile / ((long long)p.n_tiles * p.m_tiles));
+                for (int ks = 0; ks < ksteps; ++ks, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1u;
+                    bl::mbar_wait(&empty[s], ph ^ 1u);
+                    bl::mbar_arrive_expect_tx(&full[s], stage_bytes);
+                    uint8_t* dst = tiles + (size_t)s * stage_bytes;
+                    const int row = c * p.T + ks * p.KT;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        bl::tma_load_2d(dst + j * box_bytes, &p.map_a, &full[s], mt * 128 + j * 32, row);
+                    for (uint32_t j = 0; j < nb_blocks; ++j)
+                        bl::tma_load_2d(dst + a_bytes + j * box_bytes, &p.map_b, &full[s],
+                                        nt * p.BN + (int)j * 32, row);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = bl::umma_idesc_tf32(128, (uint32_t)p.BN, 1, 1);
+        uint32_t it = 0, tcount = 0;
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            const uint32_t buf = tcount & 1u;
+            const uint32_t tph = (tcount >> 1) & 1u;
+            bl::mbar_wait(&tempty[buf], tph ^ 1u);             // epilogue drained this accumulator
+            bl::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * 256u;
+            for (int ks = 0; ks < ksteps; ++ks, ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (it / p.stages) & 1u;
+                bl::mbar_wait(&full[s], ph);
+                bl::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a0 = bl::smem_u32(tiles + (size_t)s * stage_bytes);
+                    const uint32_t b0 = a0 + a_bytes;
+                    for (int ka = 0; ka < p.KT / 8; ++ka) {    // one 8-row K atom (1024 B) per MMA
+                        const uint64_t ad = bl::umma_smem_desc(a0 + ka * 1024u, box_bytes, 1024);
+                        const uint64_t bd = bl::umma_smem_desc(b0 + ka * 1024u, box_bytes, 1024);
+                        bl::umma_tf32(d_tmem, ad, bd, idesc, (ks > 0 || ka > 0) ? 1u : 0u);
+                    }
+                    bl::umma_commit(&empty[s]);
+                    if (ks == ksteps - 1) bl::umma_commit(&tfull[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================= epilogue =================
+        const int q = warp & 3;
+        uint32_t tcount = 0;
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            const int nt = (int)(tile % p.n_tiles);
+            const int mt = (int)((tile / p.n_tiles) % p.m_tiles);
+            const int c = (int)(tile / ((long long)p.n_tiles * p.m_tiles));
+            const uint32_t buf = tcount & 1u;
+            const uint32_t tph = (tcount >> 1) & 1u;
+            bl::mbar_wait(&tfull[buf], tph);
+            bl::tc_fence_after();
+            const int m = mt * 128 + q * 32 + lane;
+            float* orow = p.out + (long long)c * p.batch_stride + (long long)m * p.N;
+            for (int cb = 0; cb < p.BN; cb += 32) {
+                float v[32];
+                bl::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u + (uint32_t)cb, v);
+                const int n0 = nt * p.BN + cb;
+                if (m < p.M && n0 < p.N) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = bl_sanitize(p.alpha * v[j]);
+                    if (p.vec_ok && n0 + 32 <= p.N) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(orow + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + j < p.N) orow[n0 + j] = v[j];
+                    }
+                }
+            }
+            bl::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) bl::mbar_arrive(&tempty[buf]);
+        }
+    }
+    bl::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) bl::tmem_dealloc(tmem_base, 512);
+}
+}  // namespace
+
+extern "C" int bl_grouped_wgrad(const float* a, const float* b, float* out, int n_clients, int T, int M, int N,
+                                long long batch_stride, float alpha, int num_sms, void* stream) {
+    if (M % 4 != 0 || N % 4 != 0 || T % 8 != 0) return -1;           // TMA stride / box constraints
+    if (((uintptr_t)a) % 16 != 0 || ((uintptr_t)b) % 16 != 0) return -1;
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_clients = n_clients; p.T = T; p.M = M; p.N = N;
+    p.KT = (T % 32 == 0) ? 32 : (T % 16 == 0 ? 16 : 8);
+    int bn = (N + 31) / 32 * 32;
+    if (bn > 256) bn = 256;
+    p.BN = bn;
+    p.m_tiles = (M + 127) / 128;
+    p.n_tiles = (N + bn - 1) / bn;
+    p.alpha = alpha;
+    p.out = out;
+    p.batch_stride = batch_stride;
+    p.vec_ok = (((uintptr_t)out) % 16 == 0) && (batch_stride % 4 == 0) && (N % 4 == 0);
+    const uint64_t rows = (uint64_t)n_clients * T;
+    {
+        uint64_t dims[2] = {(uint64_t)M, rows};
+        uint64_t strides[1] = {(uint64_t)M * 4};
+        uint32_t box[2] = {32, (uint32_t)p.KT};
+        int r = bl::make_tmap_f32(&p.map_a, a, 2, dims, strides, box);
+        if (r != 0) return 1000 + r;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)N, rows};
+        uint64_t strides[1] = {(uint64_t)N * 4};
+        uint32_t box[2] = {32, (uint32_t)p.KT};
+        int r = bl::make_tmap_f32(&p.map_b, b, 2, dims, strides, box);
+        if (r != 0) return 1000 + r;
+    }
+    const size_t stage_bytes = (size_t)(4 + bn / 32) * p.KT * 128;
+    int stages = (int)((200 * 1024) / stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages < 2) return -2;
+    p.stages = stages;
+    const size_t smem = stages * stage_bytes + (2 * stages + 5) * sizeof(uint64_t) + 16;
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const long long total = (long long)n_clients * p.m_tiles * p.n_tiles;
+    int grid = num_sms > 0 ? num_sms : 148;
+    if ((long long)grid > total) grid = (int)total;
+    wgrad_tcgen05_kernel<<<grid, kWThreads, smem, (cudaStream_t)stream>>>(p);
+    return (int)cudaGetLastError();
+}

@@ -125,9 +125,10 @@ class _ConvFn(torch.autograd.Function):
         cols = F.unfold(x, (kh, kw), dilation=dilation, padding=padding, stride=stride)
         K = cols.shape[1]
         L = Ho * Wo
-        a = gy.reshape(n, B, Cout, L).permute(0, 2, 1, 3).reshape(n, Cout, B * L)     # [n, Cout, T]
+        # both operands row-major over the client's T = B*L rows ("MN-major" for the tensor cores)
+        a_t = gy.reshape(n, B, Cout, L).permute(0, 1, 3, 2).reshape(n, B * L, Cout)   # [n, T, Cout]
         b = cols.view(n, B, K, L).permute(0, 1, 3, 2).reshape(n, B * L, K)            # [n, T, K]
-        sink.put_bmm(ctx.wname, a, b)
+        sink.put_bmm(ctx.wname, a_t.transpose(1, 2), b)
         if ctx.bname is not None:
             sink.put(ctx.bname, gy.reshape(n, B, Cout, L).sum((1, 3)))
         gx = None

@@ -122,7 +122,12 @@ class RoundEngine:
     def setup(self, model: nn.Module, server_opt, aggregator, loss: str, client_lr: float,
               client_optimizer="SGD", server_lr: float = 0.1) -> BladesServer:
         model.to(self.device)
-        self.gflat = FlatParams(model, device=self.device)
+        from .flat import param_layout
+        _, d = param_layout(model)
+        self.d = d
+        self._alloc_updates(len(self.local_idx), d)
+        self.gflat = FlatParams(model, device=self.device,
+                                storage=self.symm.theta if self.symm is not None else None)
         if server_opt == "SGD" or server_opt is None:
             server_opt = torch.optim.SGD(model.parameters(), lr=server_lr)
         self.server = BladesServer(optimizer=server_opt, model=model, aggregator=aggregator, flat=self.gflat)
@@ -130,9 +135,6 @@ class RoundEngine:
         self.wflat = FlatParams(self.worker, device=self.device)
         self.client_opt_spec = client_optimizer
         self.worker_opt = torch.optim.SGD(self.worker.parameters(), lr=client_lr)
-        d = self.gflat.numel
-        self.d = d
-        self._alloc_updates(len(self.local_idx), d)
         for c in self.clients:
             c.set_loss(loss)
             c.device = self.device
@@ -148,7 +150,8 @@ class RoundEngine:
             self.U = self.symm.local
         else:
             self.symm = None
-            self.U = torch.zeros(max(n_local, 1), d, device=self.device, dtype=torch.float32)[:n_local]
+            ld = (d + 63) // 64 * 64          # 256 B aligned rows: 16 B vector loads + TMA strides
+            self.U = torch.zeros(max(n_local, 1), ld, device=self.device, dtype=torch.float32)[:n_local, :d]
 
     # ------------------------------------------------------------------ training
     def _stock_for_batching(self, c: BladesClient) -> bool:
@@ -293,7 +296,8 @@ class RoundEngine:
         if self.symm is not None:
             from ..parallel.sharded import ShardedMatrix
             return ShardedMatrix(self.symm, virtual=virtual)
-        return LocalMatrix(self.U, virtual=virtual, use_kernels=self.use_kernels and self.U.is_cuda)
+        return LocalMatrix(self.U, virtual=virtual, use_kernels=self.use_kernels and self.U.is_cuda,
+                           theta=self.gflat.theta)
 
     def gather_dense(self) -> torch.Tensor:
         """Dense [N, d] on every rank (escape hatch for custom callbacks/aggregators)."""

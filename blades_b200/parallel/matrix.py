@@ -74,13 +74,18 @@ class UpdateMatrix:
     n_cols: int
     device: torch.device
     virtual: Optional[VirtualRows] = None
+    #: (lr,) -> the final primitive also applies ``theta += lr * agg`` on every replica (K8 fusion)
+    server_step = None
+    step_applied = False
 
     # coordinate-wise -----------------------------------------------------------
     def mean(self) -> torch.Tensor:
         w = torch.full((self.n_rows,), 1.0 / self.n_rows, dtype=torch.float64)
         return self.combine(w)
 
-    def combine(self, weights) -> torch.Tensor: raise NotImplementedError
+    def combine(self, weights, extra: Optional[torch.Tensor] = None, extra_weight: float = 0.0) -> torch.Tensor:
+        """``sum_i w_i U[i] (+ extra_weight * extra)``."""
+        raise NotImplementedError
     def trimmed_mean(self, b: int) -> torch.Tensor: raise NotImplementedError
     def median(self) -> torch.Tensor: raise NotImplementedError
     # geometry ------------------------------------------------------------------
@@ -105,9 +110,10 @@ class LocalMatrix(UpdateMatrix):
     """
 
     def __init__(self, data: torch.Tensor, virtual: Optional[VirtualRows] = None,
-                 use_kernels: Optional[bool] = None):
+                 use_kernels: Optional[bool] = None, theta: Optional[torch.Tensor] = None):
         assert data.dim() == 2, data.shape
         self.data = data
+        self.theta = theta               # flat parameter vector for the fused server step
         self.n_rows, self.n_cols = data.shape
         self.device = data.device
         self.virtual = virtual
@@ -141,14 +147,32 @@ class LocalMatrix(UpdateMatrix):
         return self.materialize_virtual()
 
     # -- primitives -----------------------------------------------------------------
-    def combine(self, weights) -> torch.Tensor:
+    def _epilogue(self, out: torch.Tensor):
+        from ..ops import select as _s
+        if self.server_step is not None and self.theta is not None:
+            self.step_applied = True
+            return _s.make_epilogue([out.data_ptr()], [self.theta.data_ptr()], self.theta.data_ptr(),
+                                    float(self.server_step[0]))
+        return _s.make_epilogue([out.data_ptr()])
+
+    def combine(self, weights, extra: Optional[torch.Tensor] = None, extra_weight: float = 0.0) -> torch.Tensor:
         w = torch.as_tensor(np.asarray(weights, dtype=np.float64) if not torch.is_tensor(weights) else weights)
         if self.use_kernels:
-            from ..ops import combine as _k
-            return _k.row_combine(self.rows(), w)
+            from ..ops import combine as _k, select as _s
+            data = self.rows()
+            rows = _s.row_pointers(data)
+            wl = [float(x) for x in w.tolist()]
+            if extra is not None and extra_weight != 0.0:
+                extra = extra.contiguous()
+                rows, wl = rows + [extra.data_ptr()], wl + [float(extra_weight)]
+            out = torch.empty(self.n_cols, device=data.device, dtype=torch.float32)
+            _k.launch_combine(rows, wl, 0, self.n_cols, self._epilogue(out), data.device)
+            return out
         data = self.rows()
-        return (w.to(data.device, torch.float64)[:, None] * data.double()).sum(0).to(data.dtype) \
-            if data.dtype != torch.float64 else (w.to(data.device)[:, None] * data).sum(0)
+        res = (w.to(data.device, torch.float64)[:, None] * data.double()).sum(0)
+        if extra is not None and extra_weight != 0.0:
+            res = res + extra_weight * extra.to(res.device, torch.float64)
+        return res.to(data.dtype)
 
     def mean(self) -> torch.Tensor:
         if self.use_kernels:
@@ -160,18 +184,31 @@ class LocalMatrix(UpdateMatrix):
         if n - 2 * b <= 0:
             raise ValueError(f"trim {b} too large for {n} rows")
         if self.use_kernels:
-            from ..ops import select as _k
-            return _k.trimmed_mean(self.data, b, virtual=self.virtual)
+            return self._select_kernel(0, b)
         data = self.rows()
         if b == 0:
             return data.mean(0)
         srt = data.sort(dim=0).values
         return srt[b: n - b].mean(dim=0)
 
+    def _select_kernel(self, mode: int, b: int) -> torch.Tensor:
+        from ..ops import select as _s
+        data, v, n = self.data, self.virtual, self.n_rows
+        out = torch.empty(self.n_cols, device=data.device, dtype=torch.float32)
+        if v is not None and v.count:
+            byz, rep = set(v.byzantine), set(v.replaced)
+            stat = _s.row_pointers(data, [i for i in range(n) if i not in byz])
+            other = _s.row_pointers(data, [i for i in range(n) if i in byz and i not in rep])
+            _s.launch_select(stat, other, v.count, v.kind, v.param, mode, b, 0, self.n_cols,
+                             self._epilogue(out), data.device)
+        else:
+            _s.launch_select(_s.row_pointers(data), [], 0, None, 0.0, mode, b, 0, self.n_cols,
+                             self._epilogue(out), data.device)
+        return out
+
     def median(self) -> torch.Tensor:
         if self.use_kernels:
-            from ..ops import select as _k
-            return _k.median(self.data, virtual=self.virtual)
+            return self._select_kernel(1, 0)
         data = self.rows()
         n = self.n_rows
         srt = data.sort(dim=0).values

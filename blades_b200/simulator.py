@@ -242,6 +242,10 @@ class Simulator(object):
         if isinstance(agg, _BaseAggregator):
             from .aggregators.fltrust import Fltrust
             matrix = eng.make_matrix(virtual)
+            if self._opts["fuse_server_step"] and getattr(agg, "fusable_final", False) \
+                    and self.server._flat_fast_path_ok() and getattr(matrix, "use_kernels", True):
+                matrix.server_step = (self.server.current_lr(),)
+            self._last_matrix = matrix
             if isinstance(agg, Fltrust):
                 trusted = [i for i, c in enumerate(self.get_clients()) if c.is_trusted()]
                 assert len(trusted) == 1, "FLTrust needs exactly one trusted client"
@@ -279,11 +283,13 @@ class Simulator(object):
                     c = self.get_clients()[gi]
                     eng.U[eng.row_of[gi]].copy_(c._state["saved_update"])
                     c.bind_row(eng.U, eng.row_of[gi])
+        self._last_matrix = None
         aggregated = self._aggregate(virtual)
         self.last_aggregate = aggregated
         eng.timer.stop("aggregate")
         eng.timer.start("apply")
-        self.server.apply_update(aggregated)
+        if not (self._last_matrix is not None and self._last_matrix.step_applied):
+            self.server.apply_update(aggregated)      # else: already done in the kernel epilogue
         eng.timer.stop("apply")
         eng.timer.flush()
 
