@@ -23,6 +23,20 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
+#: set False to force the numpy implementations (tests compare both)
+USE_NATIVE = True
+
+
+def _native():
+    if not USE_NATIVE:
+        return None
+    try:
+        from ..ops import host
+        return host if host.available() else None
+    except Exception:
+        return None
+
+
 __all__ = [
     "sq_dists", "dist_to_combo", "krum_scores", "multi_krum_select", "weiszfeld_weights",
     "autogm_weights", "centered_clip_coeffs", "cosine_matrix", "complete_linkage_2",
@@ -54,6 +68,9 @@ def krum_scores(D: np.ndarray, f: int, n: Optional[int] = None, squared_twice: b
     """
     n = D.shape[0] if n is None else n
     k = n - f - 2
+    nat = _native()
+    if nat is not None:
+        return nat.krum_scores(D[:n, :n], f, squared_twice)
     M = D[:n, :n].copy()
     if squared_twice:
         M = M ** 2
@@ -91,6 +108,9 @@ def weiszfeld_weights(G: np.ndarray, alphas: Optional[np.ndarray] = None, maxite
     """
     n = G.shape[0]
     alphas = np.full(n, 1.0 / n) if alphas is None else np.asarray(alphas, dtype=np.float64).copy()
+    nat = _native()
+    if nat is not None:
+        return nat.weiszfeld(G, alphas, maxiter, eps, ftol, compounding)
     # starting point: plain mean of the rows (geomed.py:66)
     w = np.full(n, 1.0 / n)
     run = alphas.copy()          # the "weights" variable of the reference
@@ -120,6 +140,9 @@ def autogm_weights(G: np.ndarray, lamb: Optional[float] = None, maxiter: int = 1
     """
     n = G.shape[0]
     lamb = float(n) if lamb is None else float(lamb)
+    nat = _native()
+    if nat is not None:
+        return nat.autogm(G, lamb, maxiter, eps, ftol, sort_by_index, compounding)
     alpha = np.full(n, 1.0 / n)
     w, _ = weiszfeld_weights(G, alpha, maxiter, eps, ftol, compounding)
     dist = dist_to_combo(G, w)
@@ -155,6 +178,9 @@ def centered_clip_coeffs(G_aug: np.ndarray, tau: float, n_iter: int) -> np.ndarr
     Returns the final coefficient vector (length N+1).
     """
     n = G_aug.shape[0] - 1
+    nat = _native()
+    if nat is not None:
+        return nat.centered_clip(G_aug, tau, n_iter)
     c = np.zeros(n + 1)
     c[n] = 1.0
     for _ in range(n_iter):
@@ -188,6 +214,9 @@ def complete_linkage_2(dist: np.ndarray) -> np.ndarray:
     n = dist.shape[0]
     if n == 1:
         return np.zeros(1, dtype=np.int64)
+    nat = _native()
+    if nat is not None:
+        return nat.complete_linkage2(dist)
     D = np.array(dist, dtype=np.float64, copy=True)
     D = np.maximum(D, D.T)            # symmetrise (reference matrices are symmetric)
     np.fill_diagonal(D, np.inf)

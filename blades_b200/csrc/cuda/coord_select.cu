@@ -35,9 +35,12 @@ coord_select_kernel(const __grid_constant__ SelectParams p) {
     if (c >= p.c1) return;
     float v[NP];
     const int n = p.n_real;
+    // Issue ALL row loads back to back before the first use (rows[i >= n] alias row 0 on the host
+    // side, so no load is predicated): one DRAM/NVLink round trip per thread instead of NP.
 #pragma unroll
-    for (int i = 0; i < NP; ++i)
-        v[i] = (i < n) ? bl_sanitize(bl_ldg_stream(p.rows[i] + c)) : INFINITY;
+    for (int i = 0; i < NP; ++i) v[i] = bl_ldg_stream(p.rows[i] + c);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) v[i] = (i < n) ? bl_sanitize(v[i]) : INFINITY;
 
     // ---- attack prologue (K7): statistics of the honest rows, still in load order
     float m = 0.f;

@@ -1,0 +1,67 @@
+// Row-major im2col for the per-client weight-gradient GEMM (K9): NCHW activations ->
+// cols[(b, ho, wo)][(cin, r, s)], i.e. exactly the [n_clients*T, K] "MN-major" B operand the grouped
+// wgrad kernel consumes and with K ordered like the flattened conv weight [Cout][Cin*kh*kw].
+// (torch's F.unfold launches one small kernel per sample -- 64 000 launches for a 3200-image batch --
+// and produces the transposed [K, L] layout; this is one launch with coalesced 128 B row writes.)
+#include "common.cuh"
+
+struct Im2colParams {
+    const float* x;
+    float* out;
+    int NB, Cin, H, W, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo;
+    long long rows;     // NB*Ho*Wo
+    int K;              // Cin*kh*kw
+};
+
+constexpr int kRowsPerBlock = 8;
+
+__global__ void __launch_bounds__(256)
+im2col_rows_kernel(const __grid_constant__ Im2colParams p) {
+    __shared__ long long s_base[kRowsPerBlock];
+    __shared__ int s_h0[kRowsPerBlock], s_w0[kRowsPerBlock];
+    const long long row0 = (long long)blockIdx.x * kRowsPerBlock;
+    if (threadIdx.x < kRowsPerBlock) {
+        const long long row = row0 + threadIdx.x;
+        if (row < p.rows) {
+            const int L = p.Ho * p.Wo;
+            const long long b = row / L;
+            const int l = (int)(row - b * L);
+            const int ho = l / p.Wo, wo = l - ho * p.Wo;
+            s_base[threadIdx.x] = b * (long long)p.Cin * p.H * p.W;
+            s_h0[threadIdx.x] = ho * p.sh - p.ph;
+            s_w0[threadIdx.x] = wo * p.sw - p.pw;
+        } else {
+            s_base[threadIdx.x] = -1;
+        }
+    }
+    __syncthreads();
+    const int taps = p.kh * p.kw;
+    const long long HW = (long long)p.H * p.W;
+    for (int col = threadIdx.x; col < p.K; col += blockDim.x) {
+        const int cin = col / taps;
+        const int t = col - cin * taps;
+        const int r = t / p.kw, s = t - r * p.kw;
+        const int dh = r * p.dh, dw = s * p.dw;
+        const long long coff = cin * HW;
+#pragma unroll
+        for (int i = 0; i < kRowsPerBlock; ++i) {
+            const long long base = s_base[i];
+            if (base < 0) break;
+            const int h = s_h0[i] + dh, w = s_w0[i] + dw;
+            float v = 0.f;
+            if (h >= 0 && h < p.H && w >= 0 && w < p.W) v = __ldg(p.x + base + coff + (long long)h * p.W + w);
+            p.out[(row0 + i) * p.K + col] = v;
+        }
+    }
+}
+
+extern "C" int bl_im2col_rows(const float* x, float* out, int NB, int Cin, int H, int W, int kh, int kw, int sh,
+                              int sw, int ph, int pw, int dh, int dw, int Ho, int Wo, void* stream) {
+    Im2colParams p{x, out, NB, Cin, H, W, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo, (long long)NB * Ho * Wo,
+                   Cin * kh * kw};
+    if (p.rows <= 0) return 0;
+    const long long blocks = (p.rows + kRowsPerBlock - 1) / kRowsPerBlock;
+    if (blocks > 0x7fffffffLL) return -1;
+    im2col_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    return (int)cudaGetLastError();
+}

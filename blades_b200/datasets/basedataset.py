@@ -62,7 +62,8 @@ class BatchStream:
     def __iter__(self):
         return self
 
-    def __next__(self):
+    def next_indices(self) -> np.ndarray:
+        """Sample indices of the next mini-batch (advances the cursor)."""
         if self._perm is None:
             self._reshuffle()
         if self._pos * self.batch_size >= len(self.labels):
@@ -70,6 +71,10 @@ class BatchStream:
             self._reshuffle()
         sl = self._perm[self._pos * self.batch_size:(self._pos + 1) * self.batch_size]
         self._pos += 1
+        return sl
+
+    def __next__(self):
+        sl = self.next_indices()
         X = torch.from_numpy(np.ascontiguousarray(self.data[sl])).float()
         if self.transform:
             X = self.transform(X)

@@ -11,6 +11,7 @@ from __future__ import annotations
 from typing import Iterable, List, Optional, Sequence, Tuple
 from warnings import warn
 
+import numpy as np
 import torch
 
 __all__ = ["FLDataset"]
@@ -45,6 +46,9 @@ class FLDataset:
         ``X[len(ids), k, B, ...]`` float32 and ``y[len(ids), k, B]`` int64, in reusable pinned memory.
         All clients must yield equal batch shapes (true for the built-in generators
         unless a client's shard is smaller than one batch)."""
+        fast = self._native_gather(client_ids, num_batches, pin)
+        if fast is not None:
+            return fast
         rows = [self.get_train_data(c, num_batches) for c in client_ids]
         x0, y0 = rows[0][0]
         shape_x = (len(client_ids), num_batches) + tuple(x0.shape)
@@ -64,6 +68,53 @@ class FLDataset:
                 bx[i, j].copy_(x)
                 by[i, j].copy_(y)
         return bx, by
+
+    def _native_gather(self, client_ids, num_batches, pin):
+        """Multi-threaded C++ batch assembly (csrc/host: bl_gather_batches) straight into the pinned
+        staging buffer -- used when every stream is an untransformed float32 ``BatchStream``."""
+        from .basedataset import BatchStream
+        try:
+            from ..ops import host
+        except Exception:
+            return None
+        if not host.available():
+            return None
+        streams = [self._train_dls[c] for c in client_ids]
+        if not all(isinstance(s, BatchStream) and s.transform is None and s.data.dtype == np.float32
+                   and s.data.flags.c_contiguous and s.labels.dtype == np.int64 and s.labels.flags.c_contiguous
+                   and len(s.labels) >= s.batch_size for s in streams):
+            return None
+        bs = streams[0].batch_size
+        shp = streams[0].data.shape[1:]
+        if not all(s.batch_size == bs and s.data.shape[1:] == shp for s in streams):
+            return None
+        n, per = len(streams), num_batches * bs
+        idx = np.empty((n, per), dtype=np.int64)
+        for i, s in enumerate(streams):
+            for j in range(num_batches):
+                sl = s.next_indices()
+                if len(sl) != bs:
+                    return self._ragged_restart()
+                idx[i, j * bs:(j + 1) * bs] = sl
+        shape_x = (n, num_batches, bs) + tuple(shp)
+        shape_y = (n, num_batches, bs)
+        key = (shape_x, shape_y)
+        buf = self._pinned.get(key)
+        if buf is None:
+            can_pin = pin and torch.cuda.is_available()
+            buf = self._pinned[key] = (torch.empty(shape_x, dtype=torch.float32, pin_memory=can_pin),
+                                       torch.empty(shape_y, dtype=torch.int64, pin_memory=can_pin))
+        bx, by = buf
+        import ctypes as C
+        src_x = (C.c_void_p * n)(*[s.data.ctypes.data for s in streams])
+        src_y = (C.c_void_p * n)(*[s.labels.ctypes.data for s in streams])
+        sample_bytes = int(np.prod(shp)) * 4
+        host._lib().bl_gather_batches(C.cast(src_x, C.c_void_p), C.cast(src_y, C.c_void_p), idx.reshape(-1), n, per,
+                                      sample_bytes, bx.data_ptr(), by.data_ptr())
+        return bx, by
+
+    def _ragged_restart(self):
+        raise ValueError("ragged batch (client shard not a multiple of the batch size); use get_train_data")
 
     def state_dict(self) -> dict:
         """Data cursors for checkpoint/resume (generators that expose ``state()``)."""

@@ -121,13 +121,11 @@ class _ConvFn(torch.autograd.Function):
         NB, Cout, Ho, Wo = gy.shape
         B = NB // n
         kh, kw = weight.shape[2], weight.shape[3]
-        # im2col of the input: [NB, Cin*kh*kw, L]
-        cols = F.unfold(x, (kh, kw), dilation=dilation, padding=padding, stride=stride)
-        K = cols.shape[1]
+        from ..ops.im2col import im2col_rows
         L = Ho * Wo
         # both operands row-major over the client's T = B*L rows ("MN-major" for the tensor cores)
-        a_t = gy.reshape(n, B, Cout, L).permute(0, 1, 3, 2).reshape(n, B * L, Cout)   # [n, T, Cout]
-        b = cols.view(n, B, K, L).permute(0, 1, 3, 2).reshape(n, B * L, K)            # [n, T, K]
+        b = im2col_rows(x, (kh, kw), stride, padding, dilation, (Ho, Wo)).view(n, B * L, -1)   # [n, T, K]
+        a_t = gy.reshape(n, B, Cout, L).permute(0, 1, 3, 2).reshape(n, B * L, Cout)           # [n, T, Cout]
         sink.put_bmm(ctx.wname, a_t.transpose(1, 2), b)
         if ctx.bname is not None:
             sink.put(ctx.bname, gy.reshape(n, B, Cout, L).sum((1, 3)))

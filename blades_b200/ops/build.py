@@ -24,7 +24,7 @@ HOST_SO = os.path.join(PKG, "_host.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
-CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-fopenmp", "-Wall"]
+CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-Wall"]
 
 
 def _nvcc() -> str:
@@ -37,8 +37,9 @@ def _nvcc() -> str:
 def _stamp(paths) -> str:
     h = hashlib.sha1()
     for p in sorted(paths):
-        h.update(p.encode())
-        h.update(str(os.path.getmtime(p)).encode())
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:           # content, not mtime: snapshots copied to a GPU box keep their stamps
+            h.update(f.read())
     return h.hexdigest()[:16]
 
 
@@ -66,12 +67,15 @@ def build_cuda(force=False, verbose=False) -> str:
         subprocess.check_call([sys.executable, os.path.join(CSRC, "gen_sortnet.py"), gen])
     srcs = sorted(os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith(".cu"))
     hdr_stamp = _stamp(_headers(src_dir))
+    stamp_file = CUDA_SO + ".stamp"
+    want = _stamp(srcs) + hdr_stamp
+    if not force and os.path.exists(CUDA_SO) and os.path.exists(stamp_file) and open(stamp_file).read() == want:
+        return CUDA_SO          # up to date (content hash): nothing to do, e.g. on a GPU box snapshot
     os.makedirs(BUILD, exist_ok=True)
     nvcc = _nvcc()
     jobs, objs = [], []
     for s in srcs:
-        tag = _stamp([s]) + hdr_stamp
-        obj = os.path.join(BUILD, os.path.basename(s) + "." + tag + ".o")
+        obj = os.path.join(BUILD, os.path.basename(s) + "." + _stamp([s]) + hdr_stamp + ".o")
         objs.append(obj)
         if force or not os.path.exists(obj):
             jobs.append(([nvcc] + NVCC_FLAGS + ["-I", src_dir, "-c", s, "-o", obj], obj + ".log"))
@@ -79,13 +83,9 @@ def build_cuda(force=False, verbose=False) -> str:
         for out in ex.map(lambda j: _compile(*j), jobs):
             if verbose:
                 print(out)
-    stamp_file = CUDA_SO + ".stamp"
-    want = _stamp(objs)
-    if force or jobs or not os.path.exists(CUDA_SO) or not os.path.exists(stamp_file) \
-            or open(stamp_file).read() != want:
-        _compile([nvcc, "-shared", "-o", CUDA_SO] + objs + ["-lcudart"], os.path.join(BUILD, "link_cuda.log"))
-        with open(stamp_file, "w") as f:
-            f.write(want)
+    _compile([nvcc, "-shared", "-o", CUDA_SO] + objs + ["-lcudart"], os.path.join(BUILD, "link_cuda.log"))
+    with open(stamp_file, "w") as f:
+        f.write(want)
     return CUDA_SO
 
 

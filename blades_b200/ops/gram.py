@@ -9,7 +9,10 @@ import torch
 
 __all__ = ["gram"]
 
-PRECISION = "tf32x3"      # 'tf32' | 'tf32x3' | 'fp32' (cuBLAS fp32 reference path)
+import os
+
+#: 'tf32' | 'tf32x3' (tcgen05 kernel) | 'fp32' (cuBLAS fp32 reference path); env BLADES_GRAM overrides
+PRECISION = os.environ.get("BLADES_GRAM", "tf32x3")
 
 
 def gram(data: torch.Tensor, extra: Optional[torch.Tensor] = None, precision: Optional[str] = None) -> np.ndarray:

@@ -48,8 +48,8 @@ def launch_select(stat_rows: Sequence[int], other_rows: Sequence[int], n_virtual
     total = n_real + n_virtual
     if n_real <= 128:
         p = _structs.SelectParams()
-        for i, r in enumerate(rows):
-            p.rows[i] = r
+        for i in range(128):          # unused slots alias row 0: the kernel loads them unpredicated
+            p.rows[i] = rows[i] if i < n_real else rows[0]
         fn = lib.bl_coord_select
     else:
         assert total <= _structs.MAX_ROWS, f"at most {_structs.MAX_ROWS} rows"

@@ -13,7 +13,10 @@ import torch
 
 __all__ = ["grouped_wgrad"]
 
-_USE_KERNEL = True
+import os
+
+#: BLADES_WGRAD=cublas forces the library fallback (A/B comparisons, debugging)
+_USE_KERNEL = os.environ.get("BLADES_WGRAD", "tcgen05") != "cublas"
 
 
 def grouped_wgrad(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:

@@ -136,7 +136,7 @@ def test_gram(n, d):
     ref = (U.double() @ U.double().T).cpu().numpy()
     for prec in ("tf32x3", "tf32"):
         G = gram.gram(U, precision=prec)
-        tol = 2e-6 if prec == "tf32x3" else 2e-3
+        tol = 1e-5 if prec == "tf32x3" else 2e-3
         scale = np.abs(ref).max()
         assert np.abs(G - ref).max() <= tol * scale, (prec, np.abs(G - ref).max() / scale)
     extra = torch.randn(d, device=_dev()) * 0.01
@@ -144,20 +144,77 @@ def test_gram(n, d):
     full = torch.cat([U, extra[None]]).double()
     ref = (full @ full.T).cpu().numpy()
     assert G.shape == (n + 1, n + 1)
-    assert np.abs(G - ref).max() <= 2e-6 * np.abs(ref).max()
+    assert np.abs(G - ref).max() <= 1e-5 * np.abs(ref).max()
 
 
-def test_grouped_wgrad():
+@pytest.mark.parametrize("n,M,T,N", [(5, 64, 32, 576), (3, 128, 2048, 576), (7, 512, 32, 4608), (2, 64, 8192, 148),
+                                     (4, 256, 128, 2304), (1, 128, 64, 128), (3, 100, 40, 260), (2, 64, 32, 28)])
+def test_grouped_wgrad(n, M, T, N):
     from blades_b200.ops import wgrad
-    n, M, K, N, d = 5, 64, 32, 576, 64 * 576 + 128
-    a = torch.randn(n, M, K, device=_dev())
-    b = torch.randn(n, K, N, device=_dev())
+    d = M * N + 192
+    a_t = torch.randn(n, T, M, device=_dev())          # [n, T, M] row-major (how activations arrive)
+    b = torch.randn(n, T, N, device=_dev())
     U = torch.zeros(n, d, device=_dev())
     out = U[:, 64: 64 + M * N].view(n, M, N)
-    wgrad.grouped_wgrad(a, b, out, -0.1)
-    ref = -0.1 * (a.double() @ b.double())
-    assert torch.allclose(out.double(), ref, atol=2e-2, rtol=2e-3)
+    wgrad.grouped_wgrad(a_t.transpose(1, 2), b, out, -0.1)
+    ref = -0.1 * (a_t.double().transpose(1, 2) @ b.double())
+    err = (out.double() - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item() + 1e-4, err
     assert U[:, :64].abs().sum() == 0 and U[:, 64 + M * N:].abs().sum() == 0
+
+
+def test_grouped_wgrad_uses_tcgen05():
+    from blades_b200.ops import _loader, wgrad
+    a_t = torch.randn(2, 64, 128, device=_dev())
+    b = torch.randn(2, 64, 256, device=_dev())
+    out = torch.empty(2, 128, 256, device=_dev())
+    before = _loader.LAUNCHES
+    wgrad.grouped_wgrad(a_t.transpose(1, 2), b, out, 1.0)
+    assert _loader.LAUNCHES == before + 1, "tcgen05 wgrad kernel did not run"
+
+
+@pytest.mark.parametrize("shape", [(6, 3, 32, 32, 64, 7, 2, 3), (8, 64, 8, 8, 64, 3, 1, 1), (4, 128, 4, 4, 256, 3, 2, 1),
+                                   (4, 256, 2, 2, 512, 1, 2, 0), (5, 512, 1, 1, 512, 3, 1, 1)])
+def test_im2col_rows(shape):
+    import torch.nn.functional as F
+    from blades_b200.ops.im2col import im2col_rows
+    NB, Cin, H, W, Cout, k, s, p = shape
+    x = torch.randn(NB, Cin, H, W, device=_dev())
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    got = im2col_rows(x, (k, k), (s, s), (p, p), (1, 1), (Ho, Wo))
+    ref = F.unfold(x, (k, k), padding=p, stride=s).transpose(1, 2).reshape(NB * Ho * Wo, Cin * k * k)
+    assert torch.equal(got, ref)
+
+
+def test_batched_engine_on_gpu_matches_per_client():
+    """Client-batched fedsgd (tcgen05 wgrad + im2col kernels) vs per-client autograd on the GPU."""
+    import copy
+    from blades_b200.engine import batched as cb
+    from blades_b200.engine.flat import FlatParams
+    from blades_b200.models import resnet18
+    torch.manual_seed(0)
+    model = resnet18(10).to(_dev())
+    n, B, lr = 4, 32, 0.1
+    X = torch.randn(n, B, 3, 32, 32, device=_dev())
+    y = torch.randint(0, 10, (n, B), device=_dev())
+    rows = []
+    for c in range(n):
+        m = copy.deepcopy(model)
+        m.train()
+        loss = torch.nn.functional.cross_entropy(m(X[c]), y[c])
+        g = torch.autograd.grad(loss, [p for p in m.parameters()])
+        rows.append(torch.cat([-lr * t.reshape(-1) for t in g]))
+    ref = torch.stack(rows)
+    flat = FlatParams(model)
+    U = torch.zeros(n, flat.numel, device=_dev())
+    sink = cb.GradSink(U, flat.specs, n, alpha=-lr)
+    model.train()
+    with cb.client_batched(model, sink, n * B):
+        logits = model(X.reshape(n * B, 3, 32, 32))
+        loss, _ = cb.batched_loss(logits, y.reshape(-1), n, torch.full((n,), 1e6, device=_dev()))
+        loss.backward()
+    rel = (U - ref).norm() / ref.norm()
+    assert rel < 2e-2, rel            # tf32 GEMMs on both sides
 
 
 def test_simulator_gpu_matches_cpu_oracle(tmp_path):
