@@ -127,13 +127,19 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
 //   stride SBO; LBO is unused (set to 1).  Advancing along K inside the 128 B row = add bytes>>4.
 // MN-major, SWIZZLE_128B: 128 B contiguous along M/N, 8 k-rows per atom; LBO = stride between
 //   128 B column blocks, SBO = stride between 8-row k atoms.
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   layout 1 = SWIZZLE_128B_BASE32B: the ONLY layout tcgen05 accepts for MN-major tf32 operands: 128 B
+//   contiguous along M/N, 32 B chunks XOR-swizzled with (k row & 3), K atoms of 4 rows (512 B) -- what
+//   TMA produces with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  SBO = stride between 4-row K atoms.
+constexpr uint32_t kLayoutSw128 = 2;
+constexpr uint32_t kLayoutSw128Base32B = 1;
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = kLayoutSw128) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
     d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
     d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
     d |= 1ull << 46;
-    d |= 2ull << 61;
+    d |= static_cast<uint64_t>(layout_type) << 61;
     return d;
 }
 // Instruction descriptor (32 bit) for kind::tf32, fp32 accumulate:
@@ -177,7 +183,8 @@ inline EncodeTiledFn encode_tiled_fn() {
 // fp32 tensor map, SWIZZLE_128B, zero OOB fill.  dims/strides innermost first; strides in bytes for
 // dims 1..rank-1 (multiples of 16 B).
 inline int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                         const uint64_t* strides_bytes, const uint32_t* box) {
+                         const uint64_t* strides_bytes, const uint32_t* box,
+                         CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return -100;
     cuuint64_t gd[5], gs[5];
@@ -185,7 +192,7 @@ inline int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uin
     for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return (int)r;
 }

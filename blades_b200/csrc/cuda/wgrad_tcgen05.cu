@@ -8,7 +8,8 @@
 // SGD step + update diff + nan_to_num + save_update of the reference (client.py:127-131,178-198):
 // alpha = -lr.  The problem is output-bound (K = T is 32..8192 while each client writes M*N floats),
 // so the kernel is organised around streaming 128x256 fp32 tiles out of TMEM at HBM write speed:
-//   warp 0   TMA producer: per stage 4 (A) + BN/32 (B) boxes of [KT rows x 128 B], SWIZZLE_128B
+//   warp 0   TMA producer: per stage 4 (A) + BN/32 (B) boxes of [KT rows x 128 B], SWIZZLE_128B_ATOM_32B
+//            (the only smem layout tcgen05 accepts for MN-major tf32 operands)
 //   warp 1   MMA issuer: tcgen05.mma.kind::tf32, M=128, N=BN, one K=8 atom per instruction,
 //            accumulators double-buffered in TMEM (2 x 256 columns)
 //   warps 2-5 epilogue: tcgen05.ld -> scale/sanitise -> 128 B-per-thread global stores
@@ -17,6 +18,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cstring>
+#include <cstdlib>
 
 struct WgradParams {
     CUtensorMap map_a;       // 2D: (M, n_clients*T), box (32, KT)
@@ -30,6 +32,7 @@ struct WgradParams {
     float* out;              // out[c*batch_stride + m*N + n]
     long long batch_stride;
     int vec_ok;              // 16 B aligned stores possible
+    int dbg_swap;            // debug: swap LBO/SBO in the operand descriptors
 };
 
 namespace {
@@ -110,8 +113,11 @@ wgrad_tcgen05_kernel(const __grid_constant__ WgradParams p) {
                     const uint32_t a0 = bl::smem_u32(tiles + (size_t)s * stage_bytes);
                     const uint32_t b0 = a0 + a_bytes;
                     for (int ka = 0; ka < p.KT / 8; ++ka) {    // one 8-row K atom (1024 B) per MMA
-                        const uint64_t ad = bl::umma_smem_desc(a0 + ka * 1024u, box_bytes, 1024);
-                        const uint64_t bd = bl::umma_smem_desc(b0 + ka * 1024u, box_bytes, 1024);
+                        // MN-major tf32: SWIZZLE_128B_BASE32B; LBO = stride between 32-float column
+                        // blocks, SBO = stride between 4-row K atoms (rows are contiguous: 512 B)
+                        const uint32_t lbo = p.dbg_swap ? 512u : box_bytes, sbo = p.dbg_swap ? box_bytes : 512u;
+                        const uint64_t ad = bl::umma_smem_desc(a0 + ka * 1024u, lbo, sbo, bl::kLayoutSw128Base32B);
+                        const uint64_t bd = bl::umma_smem_desc(b0 + ka * 1024u, lbo, sbo, bl::kLayoutSw128Base32B);
                         bl::umma_tf32(d_tmem, ad, bd, idesc, (ks > 0 || ka > 0) ? 1u : 0u);
                     }
                     bl::umma_commit(&empty[s]);
@@ -180,19 +186,23 @@ extern "C" int bl_grouped_wgrad(const float* a, const float* b, float* out, int 
     p.out = out;
     p.batch_stride = batch_stride;
     p.vec_ok = (((uintptr_t)out) % 16 == 0) && (batch_stride % 4 == 0) && (N % 4 == 0);
+    {
+        const char* e = getenv("BLADES_WGRAD_SWAP");
+        p.dbg_swap = (e && e[0] == '1') ? 1 : 0;
+    }
     const uint64_t rows = (uint64_t)n_clients * T;
     {
         uint64_t dims[2] = {(uint64_t)M, rows};
         uint64_t strides[1] = {(uint64_t)M * 4};
         uint32_t box[2] = {32, (uint32_t)p.KT};
-        int r = bl::make_tmap_f32(&p.map_a, a, 2, dims, strides, box);
+        int r = bl::make_tmap_f32(&p.map_a, a, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (r != 0) return 1000 + r;
     }
     {
         uint64_t dims[2] = {(uint64_t)N, rows};
         uint64_t strides[1] = {(uint64_t)N * 4};
         uint32_t box[2] = {32, (uint32_t)p.KT};
-        int r = bl::make_tmap_f32(&p.map_b, b, 2, dims, strides, box);
+        int r = bl::make_tmap_f32(&p.map_b, b, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (r != 0) return 1000 + r;
     }
     const size_t stage_bytes = (size_t)(4 + bn / 32) * p.KT * 128;

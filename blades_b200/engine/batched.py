@@ -142,6 +142,16 @@ class _ClientBNFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, sink, wname, bname, eps):
         n = sink.n
         NB, C, H, W = x.shape
+        ctx.sink, ctx.wname, ctx.bname = sink, wname, bname
+        ctx.fused = False
+        if x.is_cuda:
+            from ..ops import client_bn as kbn
+            xc = x.contiguous()
+            if kbn.supported(xc) and sink.out.dtype == torch.float32:
+                y, mean, rstd = kbn.forward(xc, weight, bias, n, eps)
+                ctx.save_for_backward(xc, mean, rstd, weight)
+                ctx.fused = True
+                return y
         x5 = x.view(n, NB // n, C, H * W)
         var, mean = torch.var_mean(x5, dim=(1, 3), unbiased=False, keepdim=True)
         rstd = torch.rsqrt(var + eps)
@@ -154,9 +164,16 @@ class _ClientBNFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy):
-        xhat, rstd, weight = ctx.saved_tensors
         sink: GradSink = ctx.sink
         n = sink.n
+        if ctx.fused:
+            from ..ops import client_bn as kbn
+            x, mean, rstd, weight = ctx.saved_tensors
+            gx = kbn.backward(gy, x, mean, rstd, weight, n, sink.view(ctx.wname), sink.view(ctx.bname),
+                              sink.alpha, ctx.needs_input_grad[0])
+            sink.written.update((ctx.wname, ctx.bname))
+            return gx, None, None, None, None, None, None
+        xhat, rstd, weight = ctx.saved_tensors
         NB, C, H, W = gy.shape
         g5 = gy.reshape(n, NB // n, C, H * W)
         dbeta = g5.sum((1, 3))                      # [n, C]

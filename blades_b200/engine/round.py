@@ -133,6 +133,11 @@ class RoundEngine:
         self.server = BladesServer(optimizer=server_opt, model=model, aggregator=aggregator, flat=self.gflat)
         self.worker = copy.deepcopy(model)
         self.wflat = FlatParams(self.worker, device=self.device)
+        # 'SGD' | optimizer class / factory ``f(params, lr=...)``.  An optimizer *instance* (what the
+        # reference's scripts pass, scripts/cifar10.py:43-55) is ignored like in the reference (quirk
+        # Q2: clients always run plain SGD; the instance only drives the lr scheduler).
+        if isinstance(client_optimizer, torch.optim.Optimizer):
+            client_optimizer = "SGD"
         self.client_opt_spec = client_optimizer
         self.worker_opt = torch.optim.SGD(self.worker.parameters(), lr=client_lr)
         for c in self.clients:
@@ -296,6 +301,11 @@ class RoundEngine:
         if self.symm is not None:
             from ..parallel.sharded import ShardedMatrix
             return ShardedMatrix(self.symm, virtual=virtual)
+        if self.world.distributed:
+            # no symmetric memory (CPU / gloo): gather the rows; every rank aggregates identically
+            dense = self.gather_dense()
+            return LocalMatrix(dense, virtual=virtual, use_kernels=self.use_kernels and dense.is_cuda,
+                               theta=self.gflat.theta)
         return LocalMatrix(self.U, virtual=virtual, use_kernels=self.use_kernels and self.U.is_cuda,
                            theta=self.gflat.theta)
 

@@ -36,6 +36,8 @@ def launch_gram(blocks: Sequence[Tuple[int, int, int]], d: int, col0: int, col1:
                                     C.c_int, C.c_int, C.c_int, C.c_void_p]
     code = lib.bl_gram_tcgen05(C.cast(arr, C.c_void_p), len(blocks), d, col0, col1, out.data_ptr(),
                                out.stride(0), 1 if split3 else 0, _num_sms(device), _loader.stream_ptr(device))
+    if code == -7:                       # 3xTF32 staging does not fit in shared memory for this row count
+        return None
     _loader.check(code, "gram_tcgen05")
     _loader.count_launch()
     return starts
@@ -72,6 +74,8 @@ def gram_tcgen05(lib, data: torch.Tensor, extra: Optional[torch.Tensor], precisi
     ldg = (total_pad + 31) // 32 * 32
     out = torch.zeros(tile_rows, ldg, device=data.device, dtype=torch.float32)
     starts = launch_gram(blocks, d, 0, d, out, precision == "tf32x3", data.device)
+    if starts is None:
+        return None
     idx = []
     for (ptr, ld, rows), s in zip(blocks, starts):
         idx += list(range(s, s + rows))

@@ -1,0 +1,64 @@
+"""Launchers for the fused per-client BatchNorm kernels (csrc/cuda/client_bn.cu)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _loader
+
+
+class ClientBNParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("gy", C.c_void_p), ("y", C.c_void_p), ("gamma", C.c_void_p),
+                ("beta", C.c_void_p), ("mean", C.c_void_p), ("rstd", C.c_void_p), ("dgamma", C.c_void_p),
+                ("dbeta", C.c_void_p), ("ld", C.c_longlong), ("n", C.c_int), ("B", C.c_int), ("C", C.c_int),
+                ("HW", C.c_int), ("eps", C.c_float), ("alpha", C.c_float)]
+
+
+_checked = False
+
+
+def supported(x: torch.Tensor) -> bool:
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous()):
+        return False
+    hw = x.shape[2] * x.shape[3]
+    return 1 <= hw <= 256 and (hw & (hw - 1)) == 0
+
+
+def _lib():
+    global _checked
+    lib = _loader.cuda_lib()
+    if not _checked:
+        assert lib.bl_sizeof_bn_params() == C.sizeof(ClientBNParams)
+        _checked = True
+    return lib
+
+
+def forward(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, n: int, eps: float
+            ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    NB, Cc, H, W = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(n, Cc, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(n, Cc, device=x.device, dtype=torch.float32)
+    p = ClientBNParams(x.data_ptr(), None, y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(),
+                       rstd.data_ptr(), None, None, 0, n, NB // n, Cc, H * W, float(eps), 1.0)
+    _loader.check(_lib().bl_client_bn_fwd(C.byref(p), _loader.stream_ptr(x.device)), "client_bn_fwd")
+    _loader.count_launch()
+    return y, mean, rstd
+
+
+def backward(gy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor,
+             n: int, dgamma_view: torch.Tensor, dbeta_view: torch.Tensor, alpha: float, need_dx: bool
+             ) -> Optional[torch.Tensor]:
+    """``dgamma_view`` / ``dbeta_view``: strided ``[n, C]`` windows of the update matrix (row stride ld)."""
+    NB, Cc, H, W = x.shape
+    gy = gy.contiguous()
+    dx = torch.empty_like(x) if need_dx else None
+    assert dgamma_view.stride(1) == 1 and dgamma_view.stride(0) == dbeta_view.stride(0)
+    p = ClientBNParams(x.data_ptr(), gy.data_ptr(), dx.data_ptr() if need_dx else None, gamma.data_ptr(), None,
+                       mean.data_ptr(), rstd.data_ptr(), dgamma_view.data_ptr(), dbeta_view.data_ptr(),
+                       dgamma_view.stride(0), n, NB // n, Cc, H * W, 0.0, float(alpha))
+    _loader.check(_lib().bl_client_bn_bwd(C.byref(p), _loader.stream_ptr(x.device)), "client_bn_bwd")
+    _loader.count_launch()
+    return dx

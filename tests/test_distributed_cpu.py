@@ -1,0 +1,69 @@
+"""Multi-process (gloo, world_size 2/3) runs of the SPMD simulator must reproduce the single-process
+result: client->shard split, row gathering, replicated server state, distributed evaluation."""
+import os
+import socket
+import sys
+import tempfile
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _run(rank, world, port, agg, attack, out_dir, local_steps):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    torch.set_num_threads(1)
+    from blades_b200 import Simulator
+    from blades_b200.comm.group import init_world, shutdown
+    from blades_b200.datasets import synthetic_fldataset
+    from blades_b200.models import MLP
+    init_world(use_cuda=False)
+    ds = synthetic_fldataset(7, shape=(28, 28), train_bs=8, train_per_client=32, test_per_client=16, seed=3,
+                             separation=2.0)
+    kws = {"num_clients": 7, "num_byzantine": 2} if attack == "alie" else None
+    sim = Simulator(ds, num_byzantine=2 if attack else 0, attack=attack, attack_kws=kws, aggregator=agg,
+                    aggregator_kws={"nb": 2} if agg == "trimmedmean" else None,
+                    log_path=os.path.join(out_dir, "logs"), seed=1, progress=False)
+    torch.manual_seed(5)
+    m = MLP()
+    sim.run(m, global_rounds=3, local_steps=local_steps, server_lr=1.0, client_lr=0.1, validate_interval=3)
+    vec = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+    torch.save(vec, os.path.join(out_dir, f"theta_{world}_{rank}.pt"))
+    shutdown()
+
+
+@pytest.mark.parametrize("agg,attack,local_steps", [("trimmedmean", "alie", 1), ("geomed", "noise", 2),
+                                                    ("median", "labelflipping", 1)])
+def test_world_sizes_agree(agg, attack, local_steps, tmp_path):
+    out = str(tmp_path)
+    results = {}
+    for world in (1, 2, 3):
+        port = _free_port()
+        if world == 1:
+            ctx = mp.get_context("spawn")
+            p = ctx.Process(target=_run, args=(0, 1, port, agg, attack, out, local_steps))
+            p.start()
+            p.join(300)
+            assert p.exitcode == 0
+        else:
+            mp.spawn(_run, args=(world, port, agg, attack, out, local_steps), nprocs=world, join=True)
+        results[world] = [torch.load(os.path.join(out, f"theta_{world}_{r}.pt")) for r in range(world)]
+    base = results[1][0]
+    for world in (2, 3):
+        for r, vec in enumerate(results[world]):
+            if attack == "noise":     # per-rank RNG streams differ for the noise rows; replicas must still agree
+                assert torch.allclose(vec, results[world][0], atol=1e-6)
+            else:
+                assert torch.allclose(vec, base, atol=1e-5), (world, r, (vec - base).abs().max())

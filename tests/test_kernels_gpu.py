@@ -247,3 +247,28 @@ def test_simulator_gpu_aggregators(agg, kws, tmp_path):
     m = MLP()
     sim.run(m, global_rounds=2, local_steps=2, server_lr=1.0, client_lr=0.1, validate_interval=2)
     assert all(torch.isfinite(p).all() for p in m.parameters())
+
+
+@pytest.mark.parametrize("n,B,C,H", [(5, 32, 64, 16), (3, 32, 64, 8), (4, 16, 128, 4), (6, 32, 256, 2), (7, 32, 512, 1),
+                                     (2, 8, 24, 8)])
+def test_client_bn_kernels(n, B, C, H):
+    from blades_b200.ops import client_bn as kbn
+    x = torch.randn(n * B, C, H, H, device=_dev()) * 2 + 0.5
+    gamma = torch.rand(C, device=_dev()) + 0.5
+    beta = torch.randn(C, device=_dev())
+    gy = torch.randn_like(x)
+    assert kbn.supported(x)
+    y, mean, rstd = kbn.forward(x, gamma, beta, n, 1e-5)
+    x5 = x.double().view(n, B, C, H * H).requires_grad_(True)
+    var, mu = torch.var_mean(x5, dim=(1, 3), unbiased=False, keepdim=True)
+    xhat = (x5 - mu) / torch.sqrt(var + 1e-5)
+    yref = xhat * gamma.double().view(1, 1, C, 1) + beta.double().view(1, 1, C, 1)
+    assert torch.allclose(y.double().view_as(yref), yref, atol=1e-4, rtol=1e-4)
+    (gx_ref,) = torch.autograd.grad(yref, x5, gy.double().view_as(yref))
+    dg_ref = (gy.double().view_as(xhat) * xhat.detach()).sum((1, 3))
+    db_ref = gy.double().view_as(xhat).sum((1, 3))
+    U = torch.zeros(n, 2 * C + 64, device=_dev())
+    dx = kbn.backward(gy, x, mean, rstd, gamma, n, U[:, 8:8 + C], U[:, 8 + C:8 + 2 * C], -0.1, True)
+    assert torch.allclose(dx.double().view_as(gx_ref), gx_ref, atol=1e-4, rtol=1e-3)
+    assert torch.allclose(U[:, 8:8 + C].double(), -0.1 * dg_ref, atol=1e-3, rtol=1e-3)
+    assert torch.allclose(U[:, 8 + C:8 + 2 * C].double(), -0.1 * db_ref, atol=1e-3, rtol=1e-3)
