@@ -28,6 +28,9 @@ struct SelectParams {
     BlEpilogue ep;
 };
 
+// Pipe balance (ncu: the ALU pipe -- FMNMX/ISETP/SEL, 16 lanes/clk/SMSP -- is the limiter): the sorting
+// network has to live on the ALU pipe, so everything else is written as FFMA / FADD.SAT arithmetic for
+// the otherwise idle FMA pipe: masks are 0/1 floats, rank tests are saturating adds.
 template <int NP>
 __global__ void __launch_bounds__(128)
 coord_select_kernel(const __grid_constant__ SelectParams p) {
@@ -40,58 +43,71 @@ coord_select_kernel(const __grid_constant__ SelectParams p) {
 #pragma unroll
     for (int i = 0; i < NP; ++i) v[i] = bl_ldg_stream(p.rows[i] + c);
 #pragma unroll
-    for (int i = 0; i < NP; ++i) v[i] = (i < n) ? bl_sanitize(v[i]) : INFINITY;
+    for (int i = 0; i < NP; ++i) v[i] = bl_sanitize(v[i]);
 
-    // ---- attack prologue (K7): statistics of the honest rows, still in load order
+    // ---- attack prologue (K7): statistics of the honest rows (= the first n_stat slots), load order
     float m = 0.f;
     const int f = p.n_virtual;
+    const float fstat = (float)p.n_stat;
     if (f > 0) {
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < NP; ++i) s += (i < p.n_stat) ? v[i] : 0.f;
-        const float mu = s / (float)p.n_stat;
+        for (int i = 0; i < NP; ++i) s = fmaf(v[i], __saturatef(fstat - (float)i), s);     // mask = [i < n_stat]
+        const float mu = s / fstat;
         if (p.virt_kind == 1) {
             float q = 0.f;
 #pragma unroll
-            for (int i = 0; i < NP; ++i) { float d = v[i] - mu; q += (i < p.n_stat) ? d * d : 0.f; }
-            m = mu - p.virt_param * sqrtf(q / (float)(p.n_stat - 1));
+            for (int i = 0; i < NP; ++i) {
+                const float d = (v[i] - mu) * __saturatef(fstat - (float)i);
+                q = fmaf(d, d, q);
+            }
+            m = mu - p.virt_param * sqrtf(q / (fstat - 1.f));
         } else {
             m = -p.virt_param * mu;
         }
     }
+    // padding slots sort to the top: FLT_MAX (finite, so 0-weight products stay 0)
+#pragma unroll
+    for (int i = 0; i < NP; ++i) v[i] = (i < n) ? v[i] : FLT_MAX;
 
     SortNet<NP>::run(v);
 
     // ---- merge the virtual value with multiplicity f: r = #real values below m
     const int N = n + f;
-    int r = 0;
+    float rf = 0.f;
     if (f > 0) {
 #pragma unroll
-        for (int i = 0; i < NP; ++i) r += (v[i] < m) ? 1 : 0;
+        for (int i = 0; i < NP; ++i) rf += (v[i] < m) ? 1.f : 0.f;
+        rf = fminf(rf, (float)n);               // padding (FLT_MAX) never counts as a real value
     }
+    const float ff = (float)f;
     float agg;
     if (p.mode == 0) {
-        const int lo = p.trim_b, hi = N - p.trim_b;          // keep merged ranks [lo, hi)
+        const float lo = (float)p.trim_b, hi = (float)(N - p.trim_b);   // keep merged ranks [lo, hi)
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
-            const int pos = i + ((i >= r) ? f : 0);
-            s += (pos >= lo && pos < hi) ? v[i] : 0.f;
+            const float pos = fmaf(ff, __saturatef((float)(i + 1) - rf), (float)i);       // i + f*[i >= r]
+            const float keep = __saturatef(pos - lo + 1.f) * __saturatef(hi - pos);      // [lo <= pos < hi]
+            s = fmaf(keep, v[i], s);
         }
         if (f > 0) {
-            const int a = max(r, lo), b = min(r + f, hi);
-            if (b > a) s += m * (float)(b - a);
+            const float a = fmaxf(rf, lo), b = fminf(rf + ff, hi);
+            s = fmaf(m, fmaxf(b - a, 0.f), s);
         }
-        agg = s / (float)(hi - lo);
+        agg = s / (hi - lo);
     } else {
-        const int k0 = (N - 1) >> 1, k1 = N >> 1;
-        float a0 = (f > 0 && k0 >= r && k0 < r + f) ? m : 0.f;
-        float a1 = (f > 0 && k1 >= r && k1 < r + f) ? m : 0.f;
+        const float k0 = (float)((N - 1) >> 1), k1 = (float)(N >> 1);
+        float a0 = 0.f, a1 = 0.f;
+        if (f > 0) {
+            a0 = m * __saturatef(k0 - rf + 1.f) * __saturatef(rf + ff - k0);
+            a1 = m * __saturatef(k1 - rf + 1.f) * __saturatef(rf + ff - k1);
+        }
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
-            const int pos = i + ((i >= r) ? f : 0);
-            a0 += (pos == k0) ? v[i] : 0.f;
-            a1 += (pos == k1) ? v[i] : 0.f;
+            const float pos = fmaf(ff, __saturatef((float)(i + 1) - rf), (float)i);
+            a0 = fmaf(__saturatef(pos - k0 + 1.f) * __saturatef(k0 + 1.f - pos), v[i], a0);
+            a1 = fmaf(__saturatef(pos - k1 + 1.f) * __saturatef(k1 + 1.f - pos), v[i], a1);
         }
         agg = 0.5f * (a0 + a1);
     }

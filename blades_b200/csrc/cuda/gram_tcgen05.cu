@@ -273,8 +273,12 @@ extern "C" int bl_gram_tcgen05(const GramBlockDesc* blocks, int n_blocks, long l
     if (ksplits < 1) ksplits = 1;
     if ((long long)ksplits > nchunks) ksplits = (int)nchunks;
     const size_t smem = (size_t)stages * stage_bytes + (3 * stages + 2) * sizeof(uint64_t) + 16;
-    cudaError_t e = cudaFuncSetAttribute(gram_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(gram_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
     dim3 grid(ksplits, groups);
     gram_tcgen05_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
     return (int)cudaGetLastError();

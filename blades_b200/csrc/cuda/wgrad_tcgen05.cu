@@ -211,8 +211,12 @@ extern "C" int bl_grouped_wgrad(const float* a, const float* b, float* out, int 
     if (stages < 2) return -2;
     p.stages = stages;
     const size_t smem = stages * stage_bytes + (2 * stages + 5) * sizeof(uint64_t) + 16;
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    static bool attr_done = false;       // opt in to the full 227 KB once (not a stream op: keep it out of graph capture)
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
     const long long total = (long long)n_clients * p.m_tiles * p.n_tiles;
     int grid = num_sms > 0 ? num_sms : 148;
     if ((long long)grid > total) grid = (int)total;

@@ -1,0 +1,41 @@
+"""Multi-GPU (symmetric memory, pull-mode fused aggregation) must reproduce the single-GPU run."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+
+def _launch(nproc, out_dir, agg, attack, model, n_clients, port):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "_mgpu_worker.py"),
+           out_dir, agg, attack, model, str(n_clients)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("agg,attack,model,n", [("trimmedmean", "alie", "mlp", 10), ("median", "ipm", "mlp", 9),
+                                                ("mean", "none", "mlp", 7), ("krum", "noise", "mlp", 10),
+                                                ("geomed", "labelflipping", "mlp", 10),
+                                                ("centeredclipping", "signflipping", "mlp", 10),
+                                                ("trimmedmean", "alie", "resnet18", 10)])
+def test_sharded_equals_single(agg, attack, model, n, tmp_path):
+    ngpu = torch.cuda.device_count()
+    out = str(tmp_path)
+    sizes = [1, 2] + ([ngpu] if ngpu > 2 else [])
+    for i, w in enumerate(sizes):
+        _launch(w, out, agg, attack, model, n, 29610 + i)
+    a = None if attack == "none" else attack
+    base = torch.load(os.path.join(out, f"theta_{agg}_{a}_{model}_1_0.pt"))
+    for w in sizes[1:]:
+        vecs = [torch.load(os.path.join(out, f"theta_{agg}_{a}_{model}_{w}_{r}.pt")) for r in range(w)]
+        for v in vecs[1:]:
+            assert torch.equal(v, vecs[0]), "replicas diverged"
+        if attack == "noise":
+            continue                      # noise rows use per-rank RNG offsets
+        tol = 5e-3 if model == "resnet18" else 5e-4
+        assert torch.allclose(vecs[0], base, atol=tol, rtol=1e-2), (w, (vecs[0] - base).abs().max())
