@@ -115,6 +115,7 @@ class RoundEngine:
         self.matrix_factory: Optional[Callable] = None
         self.last_client_losses: Optional[torch.Tensor] = None
         self.kernel_launches = 0
+        self._clamps = {}
         self._graphs = {}           # (rows, lr, shape) -> (CUDAGraph, static X, static y, losses)
         self.prestaged = None       # optional (X[n,1,B,...], y[n,1,B]) already on the device
         self.h2d_bytes = 0
@@ -217,6 +218,7 @@ class RoundEngine:
         key = (tuple(rows), float(lr), tuple(X.shape))
         entry = self._graphs.get(key)
         if entry is None:
+            self._clamp_tensor(rows)
             sx, sy = X.clone(), y.clone()        # static input buffers owned by the graph
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
@@ -229,14 +231,28 @@ class RoundEngine:
             graph = torch.cuda.CUDAGraph()
             sx.copy_(X)
             sy.copy_(y)
+            from ..ops import _loader
+            before = _loader.LAUNCHES
             with torch.cuda.graph(graph):
                 losses = self._batched_step(rows, lr, sx, sy)
-            entry = self._graphs[key] = (graph, sx, sy, losses)
-        graph, sx, sy, losses = entry
+            entry = self._graphs[key] = (graph, sx, sy, losses, _loader.LAUNCHES - before)
+            _loader.count_launch(-entry[4])          # capture does not execute
+        graph, sx, sy, losses, n_native = entry
         sx.copy_(X, non_blocking=True)
         sy.copy_(y, non_blocking=True)
         graph.replay()
+        from ..ops import _loader
+        _loader.count_launch(n_native)               # our kernels inside the replayed graph
         self.last_client_losses = losses
+
+    def _clamp_tensor(self, rows: List[int]) -> torch.Tensor:
+        """Per-client loss clamps as a device tensor (cached: no H2D copy inside a graph capture)."""
+        key = tuple(rows)
+        t = self._clamps.get(key)
+        if t is None:
+            t = self._clamps[key] = torch.tensor(
+                [float(self.clients[self.local_idx[r]].loss_clamp) for r in rows], device=self.device)
+        return t
 
     def _batched_step(self, rows: List[int], lr: float, X: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         """X: [n, 1, B, ...], y: [n, 1, B] on the device (may be modified in place by client hooks)."""
@@ -245,8 +261,7 @@ class RoundEngine:
         X = X[:, 0]
         y = y[:, 0]
         B = X.shape[1]
-        clamp = torch.tensor([float(self.clients[self.local_idx[r]].loss_clamp) for r in rows],
-                             device=self.device)
+        clamp = self._clamp_tensor(rows)
         signs = []
         for j, r in enumerate(rows):
             c = self.clients[self.local_idx[r]]

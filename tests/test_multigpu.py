@@ -15,7 +15,12 @@ def _launch(nproc, out_dir, agg, attack, model, n_clients, port):
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "_mgpu_worker.py"),
            out_dir, agg, attack, model, str(n_clients)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stderr[-3000:]
+    if r.returncode != 0:
+        errs = ""
+        for f in sorted(os.listdir(out_dir)):
+            if f.startswith("error_rank"):
+                errs += f"\n--- {f}\n" + open(os.path.join(out_dir, f)).read()[-2500:]
+        raise AssertionError(errs or r.stderr[-3000:])
 
 
 @pytest.mark.parametrize("agg,attack,model,n", [("trimmedmean", "alie", "mlp", 10), ("median", "ipm", "mlp", 9),
