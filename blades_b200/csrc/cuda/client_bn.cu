@@ -122,3 +122,93 @@ extern "C" int bl_client_bn_bwd(const ClientBNParams* p, void* stream) {
     return (int)cudaGetLastError();
 }
 extern "C" int bl_sizeof_bn_params() { return (int)sizeof(ClientBNParams); }
+
+// ---------------------------------------------------------------------------------------------
+// NHWC (channels_last) variants: x is physically [n*B*HW rows][C]; a block owns (client, 32-channel tile):
+// thread = (row group 0..7, channel 0..31), so each row segment is one coalesced 128 B read; the block
+// strides over the client's R = B*HW rows three times (sum, squared deviation, normalise) -- passes two and
+// three are served by L2.  Any HW / C is supported.
+constexpr int kBnTile = 32, kBnGroups = 8;
+
+__device__ __forceinline__ float bn_group_reduce(float v, float (*red)[kBnTile]) {
+    const int ch = threadIdx.x % kBnTile, rg = threadIdx.x / kBnTile;
+    __syncthreads();
+    red[rg][ch] = v;
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kBnGroups; ++i) s += red[i][ch];
+    return s;
+}
+
+__global__ void __launch_bounds__(256)
+client_bn_nhwc_fwd_kernel(const __grid_constant__ ClientBNParams p) {
+    __shared__ float red[kBnGroups][kBnTile];
+    const int c = blockIdx.y;
+    const int ch = blockIdx.x * kBnTile + threadIdx.x % kBnTile, rg = threadIdx.x / kBnTile;
+    const bool live = ch < p.C;
+    const int R = p.B * p.HW;
+    const float* xb = p.x + (long long)c * R * p.C + ch;
+    const float m = (float)R;
+    float s = 0.f;
+    if (live) for (int r = rg; r < R; r += kBnGroups) s += xb[(long long)r * p.C];
+    const float mean = bn_group_reduce(s, red) / m;
+    float q = 0.f;
+    if (live) for (int r = rg; r < R; r += kBnGroups) { const float d = xb[(long long)r * p.C] - mean; q = fmaf(d, d, q); }
+    const float var = bn_group_reduce(q, red) / m;
+    const float rstd = rsqrtf(var + p.eps);
+    if (live) {
+        const float g = p.gamma[ch] * rstd, sh = p.beta[ch] - mean * g;
+        float* yb = p.y + (long long)c * R * p.C + ch;
+        for (int r = rg; r < R; r += kBnGroups) yb[(long long)r * p.C] = fmaf(xb[(long long)r * p.C], g, sh);
+        if (rg == 0) { p.mean[c * p.C + ch] = mean; p.rstd[c * p.C + ch] = rstd; }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+client_bn_nhwc_bwd_kernel(const __grid_constant__ ClientBNParams p) {
+    __shared__ float red[kBnGroups][kBnTile];
+    const int c = blockIdx.y;
+    const int ch = blockIdx.x * kBnTile + threadIdx.x % kBnTile, rg = threadIdx.x / kBnTile;
+    const bool live = ch < p.C;
+    const int R = p.B * p.HW;
+    const long long base = (long long)c * R * p.C + ch;
+    const float mean = live ? p.mean[c * p.C + ch] : 0.f;
+    const float rstd = live ? p.rstd[c * p.C + ch] : 0.f;
+    float sb = 0.f, sg = 0.f;
+    if (live)
+        for (int r = rg; r < R; r += kBnGroups) {
+            const float g = p.gy[base + (long long)r * p.C];
+            const float xh = (p.x[base + (long long)r * p.C] - mean) * rstd;
+            sb += g;
+            sg = fmaf(g, xh, sg);
+        }
+    const float dbeta = bn_group_reduce(sb, red);
+    const float dgamma = bn_group_reduce(sg, red);
+    if (live) {
+        if (rg == 0) {
+            p.dgamma[(long long)c * p.ld + ch] = bl_sanitize(p.alpha * dgamma);
+            p.dbeta[(long long)c * p.ld + ch] = bl_sanitize(p.alpha * dbeta);
+        }
+        if (p.y != nullptr) {
+            const float inv_m = 1.f / (float)R;
+            const float k = p.gamma[ch] * rstd;
+            for (int r = rg; r < R; r += kBnGroups) {
+                const float g = p.gy[base + (long long)r * p.C];
+                const float xh = (p.x[base + (long long)r * p.C] - mean) * rstd;
+                p.y[base + (long long)r * p.C] = k * (g - (dbeta + xh * dgamma) * inv_m);
+            }
+        }
+    }
+}
+
+extern "C" int bl_client_bn_nhwc_fwd(const ClientBNParams* p, void* stream) {
+    dim3 grid((p->C + kBnTile - 1) / kBnTile, p->n);
+    client_bn_nhwc_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+    return (int)cudaGetLastError();
+}
+extern "C" int bl_client_bn_nhwc_bwd(const ClientBNParams* p, void* stream) {
+    dim3 grid((p->C + kBnTile - 1) / kBnTile, p->n);
+    client_bn_nhwc_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+    return (int)cudaGetLastError();
+}

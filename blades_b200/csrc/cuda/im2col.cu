@@ -65,3 +65,80 @@ extern "C" int bl_im2col_rows(const float* x, float* out, int NB, int Cin, int H
     im2col_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
     return (int)cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------------------------
+// NHWC variant: x [NB, H, W, Cin] (the physical layout of a channels_last tensor) ->
+// cols[(b, ho, wo)][(r, s, cin)] with row stride ldk (>= K = kh*kw*Cin, padded to a multiple of 4 so the
+// wgrad kernel's TMA row stride is 16 B aligned; pad columns are written as zeros).  K is ordered like a
+// channels_last conv weight [Cout][kh][kw][Cin]; every tap is one contiguous run of Cin floats, moved as
+// float4 when Cin % 4 == 0.
+struct Im2colNhwcParams {
+    const float* x;
+    float* out;
+    int NB, Cin, H, W, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo;
+    long long rows;
+    int K, ldk;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+im2col_nhwc_kernel(const __grid_constant__ Im2colNhwcParams p) {
+    __shared__ long long s_base[kRowsPerBlock];
+    __shared__ int s_h0[kRowsPerBlock], s_w0[kRowsPerBlock];
+    const long long row0 = (long long)blockIdx.x * kRowsPerBlock;
+    if (threadIdx.x < kRowsPerBlock) {
+        const long long row = row0 + threadIdx.x;
+        if (row < p.rows) {
+            const int L = p.Ho * p.Wo;
+            const long long b = row / L;
+            const int l = (int)(row - b * L);
+            const int ho = l / p.Wo, wo = l - ho * p.Wo;
+            s_base[threadIdx.x] = b * (long long)p.H * p.W * p.Cin;
+            s_h0[threadIdx.x] = ho * p.sh - p.ph;
+            s_w0[threadIdx.x] = wo * p.sw - p.pw;
+        } else {
+            s_base[threadIdx.x] = -1;
+        }
+    }
+    __syncthreads();
+    const int groups = p.ldk / VEC;                 // ldk % VEC == 0 by construction
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        const int col = g * VEC;
+        const bool pad = col >= p.K;
+        const int tap = pad ? 0 : col / p.Cin;
+        const int cin = pad ? 0 : col - tap * p.Cin;
+        const int r = tap / p.kw, s = tap - r * p.kw;
+        const int dh = r * p.dh, dw = s * p.dw;
+#pragma unroll
+        for (int i = 0; i < kRowsPerBlock; ++i) {
+            const long long base = s_base[i];
+            if (base < 0) break;
+            const int h = s_h0[i] + dh, w = s_w0[i] + dw;
+            const bool in = !pad && h >= 0 && h < p.H && w >= 0 && w < p.W;
+            float* dst = p.out + (row0 + i) * p.ldk + col;
+            if (VEC == 4) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (in) v = __ldg(reinterpret_cast<const float4*>(p.x + base + ((long long)h * p.W + w) * p.Cin + cin));
+                *reinterpret_cast<float4*>(dst) = v;
+            } else {
+                float v = 0.f;
+                if (in) v = __ldg(p.x + base + ((long long)h * p.W + w) * p.Cin + cin);
+                *dst = v;
+            }
+        }
+    }
+}
+
+extern "C" int bl_im2col_nhwc(const float* x, float* out, int NB, int Cin, int H, int W, int kh, int kw, int sh,
+                              int sw, int ph, int pw, int dh, int dw, int Ho, int Wo, int ldk, void* stream) {
+    Im2colNhwcParams p{x, out, NB, Cin, H, W, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo, (long long)NB * Ho * Wo,
+                       Cin * kh * kw, ldk};
+    if (p.rows <= 0) return 0;
+    if (ldk < p.K) return -1;
+    const long long blocks = (p.rows + kRowsPerBlock - 1) / kRowsPerBlock;
+    if (blocks > 0x7fffffffLL) return -1;
+    const bool vec = (Cin % 4 == 0) && (ldk % 4 == 0) && (((uintptr_t)x) % 16 == 0) && (((uintptr_t)out) % 16 == 0);
+    if (vec) im2col_nhwc_kernel<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    else im2col_nhwc_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    return (int)cudaGetLastError();
+}

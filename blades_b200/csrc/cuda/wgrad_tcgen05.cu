@@ -170,8 +170,10 @@ wgrad_tcgen05_kernel(const __grid_constant__ WgradParams p) {
 }  // namespace
 
 extern "C" int bl_grouped_wgrad(const float* a, const float* b, float* out, int n_clients, int T, int M, int N,
-                                long long batch_stride, float alpha, int num_sms, void* stream) {
-    if (M % 4 != 0 || N % 4 != 0 || T % 8 != 0) return -1;           // TMA stride / box constraints
+                                long long lda, long long ldb, long long batch_stride, float alpha, int num_sms,
+                                void* stream) {
+    // a: [n*T rows][lda] (M valid columns), b: [n*T rows][ldb] (N valid columns)
+    if (lda % 4 != 0 || ldb % 4 != 0 || T % 8 != 0 || lda < M || ldb < N) return -1;   // TMA stride / box constraints
     if (((uintptr_t)a) % 16 != 0 || ((uintptr_t)b) % 16 != 0) return -1;
     WgradParams p;
     memset(&p, 0, sizeof(p));
@@ -193,14 +195,14 @@ extern "C" int bl_grouped_wgrad(const float* a, const float* b, float* out, int 
     const uint64_t rows = (uint64_t)n_clients * T;
     {
         uint64_t dims[2] = {(uint64_t)M, rows};
-        uint64_t strides[1] = {(uint64_t)M * 4};
+        uint64_t strides[1] = {(uint64_t)lda * 4};
         uint32_t box[2] = {32, (uint32_t)p.KT};
         int r = bl::make_tmap_f32(&p.map_a, a, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (r != 0) return 1000 + r;
     }
     {
         uint64_t dims[2] = {(uint64_t)N, rows};
-        uint64_t strides[1] = {(uint64_t)N * 4};
+        uint64_t strides[1] = {(uint64_t)ldb * 4};
         uint32_t box[2] = {32, (uint32_t)p.KT};
         int r = bl::make_tmap_f32(&p.map_b, b, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (r != 0) return 1000 + r;

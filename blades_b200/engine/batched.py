@@ -54,6 +54,7 @@ class GradSink:
     def __init__(self, out: torch.Tensor, specs: Sequence[ParamSpec], n_clients: int, alpha: float = 1.0):
         assert out.dim() == 2 and out.shape[0] >= n_clients
         self.out = out
+        self.channels_last = any(s.channels_last for s in specs)
         self.n = n_clients
         self.alpha = float(alpha)
         self.by_name: Dict[str, ParamSpec] = {s.name: s for s in specs}
@@ -64,7 +65,10 @@ class GradSink:
         return self.out[: self.n, s.offset: s.offset + s.numel]
 
     def put(self, name: str, grad: torch.Tensor) -> None:
-        """grad: [n, *shape] (any strides)."""
+        """grad: [n, *shape] (logical shape, any strides)."""
+        s = self.by_name[name]
+        if s.channels_last:            # physical order [Cout, kh, kw, Cin]
+            grad = grad.reshape((self.n,) + s.shape).permute(0, 1, 3, 4, 2)
         v = self.view(name)
         torch.mul(grad.reshape(self.n, -1), self.alpha, out=v)
         self.written.add(name)
@@ -107,6 +111,11 @@ class _LinearFn(torch.autograd.Function):
 class _ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, sink, wname, bname, stride, padding, dilation):
+        # NHWC end to end when the flat parameter layout is channels_last (GPU): cuDNN runs its native
+        # tensor-core kernels without layout conversions and the wgrad GEMM's [Cout] x [kh*kw*Cin] output
+        # IS the physical weight layout.
+        if x.is_cuda and sink.channels_last:
+            x = x.contiguous(memory_format=torch.channels_last)
         ctx.save_for_backward(x, weight)
         ctx.sink, ctx.wname, ctx.bname = sink, wname, bname
         ctx.conf = (stride, padding, dilation)
@@ -121,11 +130,19 @@ class _ConvFn(torch.autograd.Function):
         NB, Cout, Ho, Wo = gy.shape
         B = NB // n
         kh, kw = weight.shape[2], weight.shape[3]
-        from ..ops.im2col import im2col_rows
+        from ..ops.im2col import im2col_nhwc, im2col_rows
         L = Ho * Wo
         # both operands row-major over the client's T = B*L rows ("MN-major" for the tensor cores)
-        b = im2col_rows(x, (kh, kw), stride, padding, dilation, (Ho, Wo)).view(n, B * L, -1)   # [n, T, K]
-        a_t = gy.reshape(n, B, Cout, L).permute(0, 1, 3, 2).reshape(n, B * L, Cout)           # [n, T, Cout]
+        if sink.by_name[ctx.wname].channels_last or (sink.channels_last and kh == 1 and kw == 1):
+            # K ordered (r, s, cin) = physical order of the channels_last weight
+            if gy.is_cuda:
+                gy = gy.contiguous(memory_format=torch.channels_last)
+            cols = im2col_nhwc(x, (kh, kw), stride, padding, dilation, (Ho, Wo))      # [NB*L, K] (padded rows)
+            b = cols.as_strided((n, B * L, cols.shape[1]), (B * L * cols.stride(0), cols.stride(0), 1))
+            a_t = gy.permute(0, 2, 3, 1).reshape(n, B * L, Cout)                      # view: no copy
+        else:
+            b = im2col_rows(x, (kh, kw), stride, padding, dilation, (Ho, Wo)).view(n, B * L, -1)   # [n, T, K]
+            a_t = gy.reshape(n, B, Cout, L).permute(0, 1, 3, 2).reshape(n, B * L, Cout)           # [n, T, Cout]
         sink.put_bmm(ctx.wname, a_t.transpose(1, 2), b)
         if ctx.bname is not None:
             sink.put(ctx.bname, gy.reshape(n, B, Cout, L).sum((1, 3)))
@@ -146,8 +163,8 @@ class _ClientBNFn(torch.autograd.Function):
         ctx.fused = False
         if x.is_cuda:
             from ..ops import client_bn as kbn
-            xc = x.contiguous()
-            if kbn.supported(xc) and sink.out.dtype == torch.float32:
+            xc = x if kbn.is_nhwc(x) else x.contiguous()
+            if (kbn.is_nhwc(xc) or kbn.supported(xc)) and sink.out.dtype == torch.float32:
                 y, mean, rstd = kbn.forward(xc, weight, bias, n, eps)
                 ctx.save_for_backward(xc, mean, rstd, weight)
                 ctx.fused = True

@@ -28,9 +28,22 @@ class ParamSpec:
     shape: Tuple[int, ...]
     offset: int
     numel: int
+    #: True -> a 4-D (conv) weight stored physically as [Cout, kh, kw, Cin] (channels_last): the layout the
+    #: NHWC tensor-core convolutions and the per-client wgrad GEMM ([Cout] x [kh*kw*Cin]) produce natively.
+    channels_last: bool = False
+
+    def view(self, flat: torch.Tensor) -> torch.Tensor:
+        """Logical-shape view of this parameter inside a flat vector (last dim = d)."""
+        lead = flat.shape[:-1]
+        seg = flat[..., self.offset: self.offset + self.numel]
+        if self.channels_last:
+            co, ci, kh, kw = self.shape
+            nl = len(lead)
+            return seg.view(*lead, co, kh, kw, ci).permute(*range(nl), nl, nl + 3, nl + 1, nl + 2)
+        return seg.view(*lead, *self.shape)
 
 
-def param_layout(model: nn.Module, align: int = 1) -> Tuple[List[ParamSpec], int]:
+def param_layout(model: nn.Module, align: int = 1, channels_last: bool = False) -> Tuple[List[ParamSpec], int]:
     """Offsets of every trainable parameter in the flat vector.
 
     ``align`` > 1 would pad offsets; the public update vector is always dense
@@ -43,7 +56,8 @@ def param_layout(model: nn.Module, align: int = 1) -> Tuple[List[ParamSpec], int
             continue
         if align > 1:
             off = (off + align - 1) // align * align
-        specs.append(ParamSpec(name, tuple(p.shape), off, p.numel()))
+        cl = channels_last and p.dim() == 4 and (p.shape[2] > 1 or p.shape[3] > 1)
+        specs.append(ParamSpec(name, tuple(p.shape), off, p.numel(), cl))
         off += p.numel()
     return specs, off
 
@@ -52,11 +66,14 @@ class FlatParams:
     """Owns ``theta`` (and lazily ``grad``) and re-points module parameters at views."""
 
     def __init__(self, model: nn.Module, device=None, dtype=torch.float32,
-                 storage: Optional[torch.Tensor] = None):
+                 storage: Optional[torch.Tensor] = None, channels_last: Optional[bool] = None):
         self.model = model
-        self.specs, self.numel = param_layout(model)
         first = next(model.parameters())
         self.device = torch.device(device) if device is not None else first.device
+        # conv weights are stored channels_last on the GPU (flat coordinate order = physical order; use
+        # to_reference_order() for the reference's named_parameters() flattening)
+        self.channels_last = (self.device.type == "cuda") if channels_last is None else channels_last
+        self.specs, self.numel = param_layout(model, channels_last=self.channels_last)
         self.dtype = dtype
         if storage is None:
             storage = torch.empty(self.numel, device=self.device, dtype=dtype)
@@ -75,13 +92,31 @@ class FlatParams:
                 buf.data = buf.data.to(self.device)
             for s in self.specs:
                 p = self._by_name[s.name]
-                view = self.theta[s.offset: s.offset + s.numel].view(s.shape)
+                view = s.view(self.theta)
                 view.copy_(p.data.to(self.device, dtype))
                 p.data = view
 
     # -- views -----------------------------------------------------------------
     def view_of(self, vec: torch.Tensor, spec: ParamSpec) -> torch.Tensor:
-        return vec[..., spec.offset: spec.offset + spec.numel].view(*vec.shape[:-1], *spec.shape)
+        return spec.view(vec)
+
+    def to_reference_order(self, vec: torch.Tensor) -> torch.Tensor:
+        """Flat vector(s) in this layout -> the reference's coordinate order (each parameter flattened
+        contiguously in ``named_parameters()`` order, client.py:216-228).  Identity unless channels_last."""
+        if not self.channels_last:
+            return vec
+        out = torch.empty_like(vec)
+        for s in self.specs:
+            out[..., s.offset: s.offset + s.numel] = s.view(vec).reshape(*vec.shape[:-1], s.numel)
+        return out
+
+    def from_reference_order(self, vec: torch.Tensor) -> torch.Tensor:
+        if not self.channels_last:
+            return vec
+        out = torch.empty_like(vec)
+        for s in self.specs:
+            s.view(out).copy_(vec[..., s.offset: s.offset + s.numel].view(*vec.shape[:-1], *s.shape))
+        return out
 
     def named_views(self, vec: torch.Tensor) -> Dict[str, torch.Tensor]:
         return {s.name: self.view_of(vec, s) for s in self.specs}
@@ -91,15 +126,15 @@ class FlatParams:
         if self.grad is None:
             self.grad = torch.zeros_like(self.theta)
         for s in self.specs:
-            self._by_name[s.name].grad = self.grad[s.offset: s.offset + s.numel].view(s.shape)
+            self._by_name[s.name].grad = s.view(self.grad)
         return self.grad
 
     def realias(self) -> None:
         """Re-point parameters at ``theta`` (after someone replaced ``p.data``)."""
         for s in self.specs:
             p = self._by_name[s.name]
-            want = self.theta[s.offset: s.offset + s.numel].view(s.shape)
-            if p.data.data_ptr() != want.data_ptr():
+            want = s.view(self.theta)
+            if p.data.data_ptr() != want.data_ptr() or p.data.stride() != want.stride():
                 want.copy_(p.data)
                 p.data = want
 

@@ -18,19 +18,20 @@ def launch(lib, a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, alpha: floa
     N = b.shape[2]
     if a.dtype != torch.float32 or b.dtype != torch.float32 or out.dtype != torch.float32:
         return False
-    a_t = a.transpose(1, 2)
-    if not (a_t.is_contiguous() and b.is_contiguous()):
+    a_t = a.transpose(1, 2)                 # [n, T, M] view; rows may be padded (row stride lda >= M)
+    lda, ldb = a_t.stride(1), b.stride(1)
+    if a_t.stride(2) != 1 or b.stride(2) != 1 or a_t.stride(0) != T * lda or b.stride(0) != T * ldb:
         return False
     if out.stride(2) != 1 or out.stride(1) != N or M * N < MIN_OUTPUT_ELEMS:
         return False
-    if M % 4 or N % 4 or T % 8 or a_t.data_ptr() % 16 or b.data_ptr() % 16:
+    if lda % 4 or ldb % 4 or T % 8 or a_t.data_ptr() % 16 or b.data_ptr() % 16:
         return False
     idx = out.device.index or 0
     if idx not in _SMS:
         _SMS[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
     lib.bl_grouped_wgrad.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
-                                     C.c_longlong, C.c_float, C.c_int, C.c_void_p]
-    code = lib.bl_grouped_wgrad(a_t.data_ptr(), b.data_ptr(), out.data_ptr(), n, T, M, N, out.stride(0),
+                                     C.c_longlong, C.c_longlong, C.c_longlong, C.c_float, C.c_int, C.c_void_p]
+    code = lib.bl_grouped_wgrad(a_t.data_ptr(), b.data_ptr(), out.data_ptr(), n, T, M, N, lda, ldb, out.stride(0),
                                 float(alpha), _SMS[idx], _loader.stream_ptr(out.device))
     if code == -1 or code == -2:
         return False

@@ -26,6 +26,12 @@ def supported(x: torch.Tensor) -> bool:
     return 1 <= hw <= 256 and (hw & (hw - 1)) == 0
 
 
+def is_nhwc(x: torch.Tensor) -> bool:
+    """channels_last-contiguous 4-D fp32 CUDA tensor (C > 1 or trivially both layouts)."""
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+            and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous())
+
+
 def _lib():
     global _checked
     lib = _loader.cuda_lib()
@@ -38,12 +44,14 @@ def _lib():
 def forward(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, n: int, eps: float
             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     NB, Cc, H, W = x.shape
-    y = torch.empty_like(x)
+    nhwc = is_nhwc(x)
+    y = torch.empty_like(x)                 # preserves the memory format
     mean = torch.empty(n, Cc, device=x.device, dtype=torch.float32)
     rstd = torch.empty(n, Cc, device=x.device, dtype=torch.float32)
     p = ClientBNParams(x.data_ptr(), None, y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(),
                        rstd.data_ptr(), None, None, 0, n, NB // n, Cc, H * W, float(eps), 1.0)
-    _loader.check(_lib().bl_client_bn_fwd(C.byref(p), _loader.stream_ptr(x.device)), "client_bn_fwd")
+    fn = _lib().bl_client_bn_nhwc_fwd if nhwc else _lib().bl_client_bn_fwd
+    _loader.check(fn(C.byref(p), _loader.stream_ptr(x.device)), "client_bn_fwd")
     _loader.count_launch()
     return y, mean, rstd
 
@@ -53,12 +61,14 @@ def backward(gy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.
              ) -> Optional[torch.Tensor]:
     """``dgamma_view`` / ``dbeta_view``: strided ``[n, C]`` windows of the update matrix (row stride ld)."""
     NB, Cc, H, W = x.shape
-    gy = gy.contiguous()
+    nhwc = is_nhwc(x)
+    gy = gy.contiguous(memory_format=torch.channels_last) if nhwc else gy.contiguous()
     dx = torch.empty_like(x) if need_dx else None
     assert dgamma_view.stride(1) == 1 and dgamma_view.stride(0) == dbeta_view.stride(0)
     p = ClientBNParams(x.data_ptr(), gy.data_ptr(), dx.data_ptr() if need_dx else None, gamma.data_ptr(), None,
                        mean.data_ptr(), rstd.data_ptr(), dgamma_view.data_ptr(), dbeta_view.data_ptr(),
                        dgamma_view.stride(0), n, NB // n, Cc, H * W, 0.0, float(alpha))
-    _loader.check(_lib().bl_client_bn_bwd(C.byref(p), _loader.stream_ptr(x.device)), "client_bn_bwd")
+    fn = _lib().bl_client_bn_nhwc_bwd if nhwc else _lib().bl_client_bn_bwd
+    _loader.check(fn(C.byref(p), _loader.stream_ptr(x.device)), "client_bn_bwd")
     _loader.count_launch()
     return dx

@@ -8,7 +8,7 @@ import torch.nn.functional as F
 
 from . import _loader
 
-__all__ = ["im2col_rows"]
+__all__ = ["im2col_rows", "im2col_nhwc"]
 
 
 def im2col_rows(x: torch.Tensor, kernel, stride, padding, dilation, out_hw) -> torch.Tensor:
@@ -28,3 +28,27 @@ def im2col_rows(x: torch.Tensor, kernel, stride, padding, dilation, out_hw) -> t
                                      _loader.stream_ptr(x.device)), "im2col_rows")
     _loader.count_launch()
     return out
+
+
+def im2col_nhwc(x: torch.Tensor, kernel, stride, padding, dilation, out_hw) -> torch.Tensor:
+    """x: channels_last ``[NB, Cin, H, W]`` -> ``[NB*Ho*Wo, K]`` view of a ``[rows, ldk]`` buffer with
+    ``K = kh*kw*Cin`` ordered (r, s, cin) (= a channels_last conv weight) and ``ldk = K`` rounded up to 4."""
+    NB, Cin, H, W = x.shape
+    kh, kw = kernel
+    Ho, Wo = out_hw
+    K = Cin * kh * kw
+    if not x.is_cuda or x.dtype != torch.float32:
+        cols = F.unfold(x, kernel, dilation=dilation, padding=padding, stride=stride)      # [NB, Cin*kh*kw, L]
+        return cols.view(NB, Cin, kh * kw, Ho * Wo).permute(0, 3, 2, 1).reshape(NB * Ho * Wo, K)
+    xp = x.permute(0, 2, 3, 1)
+    if not xp.is_contiguous():
+        xp = xp.contiguous()
+    ldk = (K + 3) // 4 * 4
+    out = torch.empty(NB * Ho * Wo, ldk, device=x.device, dtype=torch.float32)
+    lib = _loader.cuda_lib()
+    lib.bl_im2col_nhwc.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 15 + [C.c_void_p]
+    _loader.check(lib.bl_im2col_nhwc(xp.data_ptr(), out.data_ptr(), NB, Cin, H, W, kh, kw, stride[0], stride[1],
+                                     padding[0], padding[1], dilation[0], dilation[1], Ho, Wo, ldk,
+                                     _loader.stream_ptr(x.device)), "im2col_nhwc")
+    _loader.count_launch()
+    return out[:, :K]

@@ -73,6 +73,19 @@ class BladesServer:
             theta.add_(update.to(theta.device, theta.dtype), alpha=self.current_lr())
             return
         self.zero_grad()
+        if self.flat is not None and getattr(self.flat, "channels_last", False):
+            # the flat vector is in physical (channels_last) order: map through the parameter specs
+            views = {id(p): s.view(update.to(self.flat.theta.device, self.flat.theta.dtype))
+                     for p, s in zip(self.flat.parameters(), self.flat.specs)}
+            for group in self.optimizer.param_groups:
+                for p in group["params"]:
+                    if p.requires_grad and id(p) in views:
+                        if p.grad is None:
+                            p.grad = views[id(p)].neg()
+                        else:
+                            torch.neg(views[id(p)], out=p.grad)
+            self.optimizer.step()
+            return
         beg = 0
         for group in self.optimizer.param_groups:
             for p in group["params"]:

@@ -31,9 +31,9 @@ def per_client_reference(model, X, y, lr, clamp=1e6):
     return torch.stack(rows)
 
 
-def batched_rows(model, X, y, lr):
+def batched_rows(model, X, y, lr, channels_last=False):
     n, B = X.shape[:2]
-    flat = FlatParams(model, dtype=next(model.parameters()).dtype)
+    flat = FlatParams(model, dtype=next(model.parameters()).dtype, channels_last=channels_last)
     U = torch.zeros(n, flat.numel, dtype=flat.dtype)
     sink = cb.GradSink(U, flat.specs, n, alpha=-lr)
     model.train()
@@ -42,7 +42,7 @@ def batched_rows(model, X, y, lr):
         loss, _ = cb.batched_loss(logits, y.reshape(-1), n, torch.full((n,), 1e6, dtype=logits.dtype))
         loss.backward()
     assert sink.written == {s.name for s in flat.specs}
-    return U
+    return flat.to_reference_order(U)
 
 
 @pytest.mark.parametrize("name", ["mlp", "resnet18", "resnet18_gn", "cct"])
@@ -64,6 +64,9 @@ def test_batched_equals_per_client(name):
     ref = per_client_reference(model, X, y, 0.1)
     got = batched_rows(copy.deepcopy(model), X, y, 0.1)
     assert torch.allclose(got, ref, atol=1e-9, rtol=1e-7), float((got - ref).abs().max())
+    if name in ("resnet18", "cct"):      # channels_last physical parameter layout (the GPU default)
+        got_cl = batched_rows(copy.deepcopy(model), X, y, 0.1, channels_last=True)
+        assert torch.allclose(got_cl, ref, atol=1e-9, rtol=1e-7), float((got_cl - ref).abs().max())
     # forward swaps are undone
     assert "forward" not in model.__dict__
 
@@ -231,3 +234,25 @@ def test_loss_decreases_and_checkpoint_resume(tmp_log, tmp_path):
     assert torch.allclose(resumed, final, atol=1e-6)
     sd = torch.load(ck, weights_only=False)
     MLP().load_state_dict(sd["model"])
+
+
+def test_channels_last_flat_layout_and_server():
+    from blades_b200.models import resnet18
+    from blades_b200.server import BladesServer
+    torch.manual_seed(0)
+    m1, m2 = resnet18(10), None
+    import copy
+    m2 = copy.deepcopy(m1)
+    f1 = FlatParams(m1, channels_last=False)
+    f2 = FlatParams(m2, channels_last=True)
+    assert torch.equal(f2.to_reference_order(f2.theta), f1.theta)
+    upd = torch.randn(f1.numel)
+    for f, m, u in ((f1, m1, upd), (f2, m2, f2.from_reference_order(upd))):
+        opt = torch.optim.SGD(m.parameters(), lr=0.5, momentum=0.9)
+        srv = BladesServer(opt, m, None, flat=f)
+        srv.apply_update(u)
+        srv.apply_update(u)
+    for p1, p2 in zip(m1.parameters(), m2.parameters()):
+        assert torch.allclose(p1, p2, atol=1e-6)
+    x = torch.randn(8, 3, 32, 32)
+    assert torch.allclose(m1(x), m2(x), atol=1e-3)

@@ -236,7 +236,7 @@ def test_batched_engine_on_gpu_matches_per_client(arch):
     X, y = Xc.to(_dev()), yc.to(_dev())
     torch_rows = _per_client_rows(gm, X, y, lr).double().cpu()
     U, flat = _batched_rows_gpu(copy.deepcopy(model).to(_dev()), X, y, lr)
-    ours = U.double().cpu()
+    ours = flat.to_reference_order(U).double().cpu()      # physical (channels_last) -> reference order
     e_torch = ((torch_rows - truth).norm() / truth.norm()).item()
     e_ours = ((ours - truth).norm() / truth.norm()).item()
     worst = []
@@ -303,3 +303,57 @@ def test_client_bn_kernels(n, B, C, H):
     assert torch.allclose(dx.double().view_as(gx_ref), gx_ref, atol=1e-4, rtol=1e-3)
     assert torch.allclose(U[:, 8:8 + C].double(), -0.1 * dg_ref, atol=1e-3, rtol=1e-3)
     assert torch.allclose(U[:, 8 + C:8 + 2 * C].double(), -0.1 * db_ref, atol=1e-3, rtol=1e-3)
+
+
+@pytest.mark.parametrize("shape", [(6, 3, 32, 32, 7, 2, 3), (8, 64, 8, 8, 3, 1, 1), (4, 128, 4, 4, 3, 2, 1),
+                                   (4, 256, 2, 2, 1, 2, 0), (5, 512, 1, 1, 3, 1, 1), (3, 6, 9, 7, 3, 1, 0)])
+def test_im2col_nhwc(shape):
+    import torch.nn.functional as F
+    from blades_b200.ops.im2col import im2col_nhwc
+    NB, Cin, H, W, k, s, p = shape
+    x = torch.randn(NB, Cin, H, W, device=_dev()).contiguous(memory_format=torch.channels_last)
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    got = im2col_nhwc(x, (k, k), (s, s), (p, p), (1, 1), (Ho, Wo))
+    ref = F.unfold(x.contiguous(), (k, k), padding=p, stride=s).view(NB, Cin, k * k, Ho * Wo)
+    ref = ref.permute(0, 3, 2, 1).reshape(NB * Ho * Wo, k * k * Cin)
+    assert got.shape == ref.shape and torch.equal(got, ref)
+    assert got.stride(0) % 4 == 0
+
+
+@pytest.mark.parametrize("n,B,C,H", [(5, 32, 64, 16), (3, 32, 64, 8), (4, 16, 128, 4), (7, 32, 512, 1), (2, 8, 24, 7)])
+def test_client_bn_nhwc_kernels(n, B, C, H):
+    from blades_b200.ops import client_bn as kbn
+    x = (torch.randn(n * B, C, H, H, device=_dev()) * 2 + 0.5).contiguous(memory_format=torch.channels_last)
+    if H == 1:
+        pytest.skip("1x1 spatial is layout-ambiguous; covered by the NCHW kernel")
+    gamma = torch.rand(C, device=_dev()) + 0.5
+    beta = torch.randn(C, device=_dev())
+    gy = torch.randn(n * B, C, H, H, device=_dev()).contiguous(memory_format=torch.channels_last)
+    assert kbn.is_nhwc(x)
+    y, mean, rstd = kbn.forward(x, gamma, beta, n, 1e-5)
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    x5 = x.double().contiguous().view(n, B, C, H * H).requires_grad_(True)
+    var, mu = torch.var_mean(x5, dim=(1, 3), unbiased=False, keepdim=True)
+    xhat = (x5 - mu) / torch.sqrt(var + 1e-5)
+    yref = xhat * gamma.double().view(1, 1, C, 1) + beta.double().view(1, 1, C, 1)
+    assert torch.allclose(y.double().contiguous().view_as(yref), yref, atol=1e-4, rtol=1e-4)
+    gyd = gy.double().contiguous().view_as(yref)
+    (gx_ref,) = torch.autograd.grad(yref, x5, gyd)
+    U = torch.zeros(n, 2 * C + 64, device=_dev())
+    dx = kbn.backward(gy, x, mean, rstd, gamma, n, U[:, 8:8 + C], U[:, 8 + C:8 + 2 * C], -0.1, True)
+    assert torch.allclose(dx.double().contiguous().view_as(gx_ref), gx_ref, atol=1e-4, rtol=1e-3)
+    assert torch.allclose(U[:, 8:8 + C].double(), -0.1 * (gyd * xhat.detach()).sum((1, 3)), atol=1e-3, rtol=1e-3)
+    assert torch.allclose(U[:, 8 + C:8 + 2 * C].double(), -0.1 * gyd.sum((1, 3)), atol=1e-3, rtol=1e-3)
+
+
+def test_wgrad_padded_rows():
+    """B operand with padded row stride (ldb > N, N % 4 != 0): the stem-conv case (K = 147)."""
+    from blades_b200.ops import wgrad
+    n, T, M, N, ld = 3, 64, 64, 147, 148
+    a_t = torch.randn(n, T, M, device=_dev())
+    store = torch.randn(n * T, ld, device=_dev())
+    b = store[:, :N].as_strided((n, T, N), (T * ld, ld, 1))
+    out = torch.zeros(n, M, N, device=_dev())
+    wgrad.grouped_wgrad(a_t.transpose(1, 2), b, out, 1.0)
+    ref = a_t.double().transpose(1, 2) @ b.double()
+    assert (out.double() - ref).abs().max() <= 2e-3 * ref.abs().max() + 1e-4
