@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cstring>
+#include <cstdlib>
 
 #define GRAM_MAX_BLOCKS 9          // 8 peers + 1 extra row block
 #define GRAM_CHUNK 32              // floats per K chunk = 128 B = one swizzle row
@@ -37,6 +38,7 @@ struct GramParams {
     int mb_per_cta;
     int stages;
     int split3;                          // 1 = 3xTF32
+    int slabs;                           // 128 B column slabs per stage (K chunk = 32*slabs floats per row)
     long long chunk0, chunk1;            // K chunk range of this launch
     float* gram;                         // [tile_rows][ld_gram] fp32, accumulated with red.add
     int ld_gram;
@@ -50,7 +52,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages][hi tile][lo tile?] then barriers
-    const uint32_t tile_bytes = (uint32_t)p.tile_rows * 128u;
+    const uint32_t slab_bytes = (uint32_t)p.tile_rows * 128u;            // one [tile_rows x 128 B] SW128 tile
+    const uint32_t tile_bytes = slab_bytes * (uint32_t)p.slabs;          // hi (or lo) part of a stage
     const uint32_t stage_bytes = tile_bytes * (p.split3 ? 2u : 1u);
     uint8_t* tiles = smem_raw;                       // dynamic smem base is 1024-aligned (checked on host)
     uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)p.stages * stage_bytes);
@@ -91,12 +94,12 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
     // rows of the tile that no TMA box covers must read as zero (hi and lo tiles, every stage)
     if (p.rows_covered < p.tile_rows) {
         const uint32_t beg = (uint32_t)p.rows_covered * 128u;
-        for (int s = 0; s < p.stages; ++s)
-            for (int t = 0; t < (p.split3 ? 2 : 1); ++t) {
-                uint8_t* base = tiles + (size_t)s * stage_bytes + (size_t)t * tile_bytes;
-                for (uint32_t off = beg + threadIdx.x * 16u; off < tile_bytes; off += kThreads * 16u)
-                    *reinterpret_cast<float4*>(base + off) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        const int n_tiles = p.stages * (p.split3 ? 2 : 1) * p.slabs;     // consecutive slabs
+        for (int t = 0; t < n_tiles; ++t) {
+            uint8_t* base = tiles + (size_t)t * slab_bytes;
+            for (uint32_t off = beg + threadIdx.x * 16u; off < slab_bytes; off += kThreads * 16u)
+                *reinterpret_cast<float4*>(base + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         bl::fence_proxy_async_smem();
     }
     bl::tc_fence_before();
@@ -108,16 +111,18 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
         if (warp == 0) {
             // ================= TMA producer =================
             if (lane == 0) {
-                const uint32_t tx = (uint32_t)p.rows_covered * 128u;
+                const uint32_t tx = (uint32_t)p.rows_covered * 128u * (uint32_t)p.slabs;
                 for (int it = 0; it < iters; ++it) {
                     const int s = it % p.stages;
                     const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
                     bl::mbar_wait(&empty[s], ph ^ 1u);
                     bl::mbar_arrive_expect_tx(&full[s], tx);
                     uint8_t* dst = tiles + (size_t)s * stage_bytes;
-                    const int c0 = (int)((kc0 + it) * GRAM_CHUNK);
-                    for (int b = 0; b < p.n_blocks; ++b)
-                        bl::tma_load_2d(dst + (size_t)p.blk_smem_row[b] * 128u, &p.maps[b], &full[s], c0, 0);
+                    const int c0 = (int)((kc0 + it) * GRAM_CHUNK * p.slabs);
+                    for (int sl = 0; sl < p.slabs; ++sl)
+                        for (int b = 0; b < p.n_blocks; ++b)
+                            bl::tma_load_2d(dst + (size_t)sl * slab_bytes + (size_t)p.blk_smem_row[b] * 128u,
+                                            &p.maps[b], &full[s], c0 + sl * GRAM_CHUNK, 0);
                 }
             }
         } else if (warp == 1) {
@@ -129,7 +134,9 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
                 bl::mbar_wait(&ready[s], ph);
                 bl::tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t hi = bl::smem_u32(tiles + (size_t)s * stage_bytes);
+                    const uint32_t hi0 = bl::smem_u32(tiles + (size_t)s * stage_bytes);
+                    for (int sl = 0; sl < p.slabs; ++sl) {
+                    const uint32_t hi = hi0 + (uint32_t)sl * slab_bytes;
                     const uint32_t lo = hi + tile_bytes;
                     for (int m = 0; m < nmb; ++m) {
                         const uint32_t a_off = (uint32_t)(mb0 + m) * 128u * 128u;
@@ -143,7 +150,7 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
                                 const uint32_t koff = (uint32_t)k * 32u;
                                 const uint64_t a_hi = bl::umma_smem_desc(hi + a_off + koff, 16, 1024);
                                 const uint64_t b_hi = bl::umma_smem_desc(hi + b_off + koff, 16, 1024);
-                                bl::umma_tf32(d_tmem, a_hi, b_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                                bl::umma_tf32(d_tmem, a_hi, b_hi, idesc, (it > 0 || sl > 0 || k > 0) ? 1u : 0u);
                                 if (p.split3) {
                                     const uint64_t a_lo = bl::umma_smem_desc(lo + a_off + koff, 16, 1024);
                                     const uint64_t b_lo = bl::umma_smem_desc(lo + b_off + koff, 16, 1024);
@@ -153,6 +160,7 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
                             }
                         }
                     }
+                    }
                     bl::umma_commit(&empty[s]);                    // smem slot reusable when MMAs retire
                     if (it == iters - 1) bl::umma_commit(done);    // accumulators final
                 }
@@ -161,12 +169,13 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
         } else {
             // ================= converter (warps 2..5) =================
             const int ct = threadIdx.x - 64;                       // 0..127
-            const uint32_t n16 = (uint32_t)p.rows_covered * 8u;    // 16 B granules in the covered tile
+            const uint32_t n16 = (uint32_t)p.rows_covered * 8u;    // 16 B granules in the covered part of a slab
             for (int it = 0; it < iters; ++it) {
                 const int s = it % p.stages;
                 const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
                 bl::mbar_wait(&full[s], ph);
-                uint8_t* hi = tiles + (size_t)s * stage_bytes;
+                for (int sl = 0; sl < p.slabs; ++sl) {
+                uint8_t* hi = tiles + (size_t)s * stage_bytes + (size_t)sl * slab_bytes;
                 uint8_t* lo = hi + tile_bytes;
                 for (uint32_t g = ct; g < n16; g += 128) {
                     float4 x = *reinterpret_cast<float4*>(hi + g * 16u);
@@ -180,6 +189,7 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
                     if (p.split3)
                         *reinterpret_cast<float4*>(lo + g * 16u) =
                             make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+                }
                 }
                 bl::fence_proxy_async_smem();                      // generic writes -> visible to UMMA
                 __syncwarp();
@@ -257,14 +267,25 @@ extern "C" int bl_gram_tcgen05(const GramBlockDesc* blocks, int n_blocks, long l
     if (p.mb_per_cta > p.n_mblk) p.mb_per_cta = p.n_mblk;
     const int groups = (p.n_mblk + p.mb_per_cta - 1) / p.mb_per_cta;
     p.split3 = split3 ? 1 : 0;
-    const size_t stage_bytes = (size_t)p.tile_rows * 128 * (p.split3 ? 2 : 1);
     const size_t budget = 227 * 1024 - 1024 - 256;
+    // wider K chunks per row (up to 4 x 128 B) = longer DRAM bursts per row visit and fewer barrier round
+    // trips per byte; keep at least 4 pipeline stages
+    int slabs = 4;
+    while (slabs > 1 && (size_t)p.tile_rows * 128 * slabs * (p.split3 ? 2 : 1) * 4 > budget) slabs >>= 1;
+    {
+        const char* e = getenv("BLADES_GRAM_SLABS");
+        if (e) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) slabs = v; }
+    }
+    p.slabs = slabs;
+    const size_t stage_bytes = (size_t)p.tile_rows * 128 * slabs * (p.split3 ? 2 : 1);
     int stages = (int)(budget / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) return -7;
     p.stages = stages;
-    p.chunk0 = col0 / GRAM_CHUNK;
-    p.chunk1 = (col1 + GRAM_CHUNK - 1) / GRAM_CHUNK;
+    const long long chunk = (long long)GRAM_CHUNK * slabs;
+    if (col0 % chunk != 0) return -2;
+    p.chunk0 = col0 / chunk;
+    p.chunk1 = (col1 + chunk - 1) / chunk;
     p.gram = gram;
     p.ld_gram = ld_gram;
     const long long nchunks = p.chunk1 - p.chunk0;

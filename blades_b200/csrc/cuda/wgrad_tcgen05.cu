@@ -37,6 +37,7 @@ struct WgradParams {
 
 namespace {
 constexpr int kWThreads = 192;
+constexpr int kEpiLd = 36;               // padded row (floats): 16 B aligned, conflict-free float4 access
 
 __global__ void __launch_bounds__(kWThreads, 1)
 wgrad_tcgen05_kernel(const __grid_constant__ WgradParams p) {
@@ -52,6 +53,7 @@ wgrad_tcgen05_kernel(const __grid_constant__ WgradParams p) {
     uint64_t* tfull = bars + 2 * p.stages;        // [2] accumulator ready
     uint64_t* tempty = bars + 2 * p.stages + 2;   // [2] accumulator drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+    float* epi = reinterpret_cast<float*>(tiles + (size_t)p.stages * stage_bytes + 256);   // 4 x [32][kEpiLd]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long total_tiles = (long long)p.n_clients * p.m_tiles * p.n_tiles;
@@ -138,25 +140,40 @@ wgrad_tcgen05_kernel(const __grid_constant__ WgradParams p) {
             const uint32_t tph = (tcount >> 1) & 1u;
             bl::mbar_wait(&tfull[buf], tph);
             bl::tc_fence_after();
-            const int m = mt * 128 + q * 32 + lane;
-            float* orow = p.out + (long long)c * p.batch_stride + (long long)m * p.N;
+            // TMEM -> registers (lane = row) -> per-warp smem transpose -> coalesced stores: every STG.128
+            // covers 4 rows x 128 contiguous bytes (a lane-per-row store would touch 32 rows x 16 B).
+            float* stg = epi + (warp - 2) * (32 * kEpiLd);
+            const int rsub = lane >> 3, csub = (lane & 7) * 4;
+            float* obase = p.out + (long long)c * p.batch_stride;
             for (int cb = 0; cb < p.BN; cb += 32) {
                 float v[32];
                 bl::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u + (uint32_t)cb, v);
                 const int n0 = nt * p.BN + cb;
-                if (m < p.M && n0 < p.N) {
+                if (n0 >= p.N) break;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = bl_sanitize(p.alpha * v[j]);
-                    if (p.vec_ok && n0 + 32 <= p.N) {
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(stg + lane * kEpiLd + j) =
+                        make_float4(bl_sanitize(p.alpha * v[j]), bl_sanitize(p.alpha * v[j + 1]),
+                                    bl_sanitize(p.alpha * v[j + 2]), bl_sanitize(p.alpha * v[j + 3]));
+                __syncwarp();
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(orow + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (n0 + j < p.N) orow[n0 + j] = v[j];
+                for (int r0 = 0; r0 < 32; r0 += 4) {
+                    const int r = r0 + rsub;
+                    const int m = mt * 128 + q * 32 + r;
+                    const float4 t = *reinterpret_cast<const float4*>(stg + r * kEpiLd + csub);
+                    if (m < p.M) {
+                        float* dst = obase + (long long)m * p.N + n0 + csub;
+                        if (p.vec_ok && n0 + csub + 4 <= p.N) {
+                            *reinterpret_cast<float4*>(dst) = t;
+                        } else {
+                            if (n0 + csub + 0 < p.N) dst[0] = t.x;
+                            if (n0 + csub + 1 < p.N) dst[1] = t.y;
+                            if (n0 + csub + 2 < p.N) dst[2] = t.z;
+                            if (n0 + csub + 3 < p.N) dst[3] = t.w;
+                        }
                     }
                 }
+                __syncwarp();
             }
             bl::tc_fence_before();
             __syncwarp();
@@ -208,11 +225,11 @@ extern "C" int bl_grouped_wgrad(const float* a, const float* b, float* out, int 
         if (r != 0) return 1000 + r;
     }
     const size_t stage_bytes = (size_t)(4 + bn / 32) * p.KT * 128;
-    int stages = (int)((200 * 1024) / stage_bytes);
+    int stages = (int)((190 * 1024) / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) return -2;
     p.stages = stages;
-    const size_t smem = stages * stage_bytes + (2 * stages + 5) * sizeof(uint64_t) + 16;
+    const size_t smem = stages * stage_bytes + 256 + 4 * 32 * kEpiLd * sizeof(float);
     static bool attr_done = false;       // opt in to the full 227 KB once (not a stream op: keep it out of graph capture)
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -28,7 +28,7 @@ def supported(x: torch.Tensor) -> bool:
 
 def is_nhwc(x: torch.Tensor) -> bool:
     """channels_last-contiguous 4-D fp32 CUDA tensor (C > 1 or trivially both layouts)."""
-    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0
             and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous())
 
 
@@ -45,6 +45,9 @@ def forward(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, n: int, ep
             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     NB, Cc, H, W = x.shape
     nhwc = is_nhwc(x)
+    if nhwc:                                # float4 parameter loads need 16 B alignment
+        gamma = gamma if gamma.data_ptr() % 16 == 0 else gamma.clone()
+        beta = beta if beta.data_ptr() % 16 == 0 else beta.clone()
     y = torch.empty_like(x)                 # preserves the memory format
     mean = torch.empty(n, Cc, device=x.device, dtype=torch.float32)
     rstd = torch.empty(n, Cc, device=x.device, dtype=torch.float32)
@@ -62,6 +65,8 @@ def backward(gy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.
     """``dgamma_view`` / ``dbeta_view``: strided ``[n, C]`` windows of the update matrix (row stride ld)."""
     NB, Cc, H, W = x.shape
     nhwc = is_nhwc(x)
+    if nhwc and gamma.data_ptr() % 16:
+        gamma = gamma.clone()
     gy = gy.contiguous(memory_format=torch.channels_last) if nhwc else gy.contiguous()
     dx = torch.empty_like(x) if need_dx else None
     assert dgamma_view.stride(1) == 1 and dgamma_view.stride(0) == dbeta_view.stride(0)
