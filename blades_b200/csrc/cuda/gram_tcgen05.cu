@@ -268,10 +268,11 @@ extern "C" int bl_gram_tcgen05(const GramBlockDesc* blocks, int n_blocks, long l
     const int groups = (p.n_mblk + p.mb_per_cta - 1) / p.mb_per_cta;
     p.split3 = split3 ? 1 : 0;
     const size_t budget = 227 * 1024 - 1024 - 256;
-    // wider K chunks per row (up to 4 x 128 B) = longer DRAM bursts per row visit and fewer barrier round
-    // trips per byte; keep at least 4 pipeline stages
-    int slabs = 4;
-    while (slabs > 1 && (size_t)p.tile_rows * 128 * slabs * (p.split3 ? 2 : 1) * 4 > budget) slabs >>= 1;
+    // wider K chunks per row (2 x 128 B) = longer DRAM bursts per row visit and half the barrier round trips
+    // per byte (measured: N=100 tf32 1.85 -> 1.55 ms, 3xTF32 2.41 -> 1.93 ms; 4 slabs gave nothing more);
+    // needs at least 3 pipeline stages to pay off
+    int slabs = 2;
+    if ((size_t)p.tile_rows * 128 * slabs * (p.split3 ? 2 : 1) * 3 > budget) slabs = 1;
     {
         const char* e = getenv("BLADES_GRAM_SLABS");
         if (e) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) slabs = v; }
