@@ -116,6 +116,8 @@ class RoundEngine:
         self.last_client_losses: Optional[torch.Tensor] = None
         self.kernel_launches = 0
         self._clamps = {}
+        self._round_graphs = {}     # (client lr, server lr) -> captured whole-round graph state
+        self.static_aggregate = None
         self._graphs = {}           # (rows, lr, shape) -> (CUDAGraph, static X, static y, losses)
         self.prestaged = None       # optional (X[n,1,B,...], y[n,1,B]) already on the device
         self.h2d_bytes = 0
@@ -244,6 +246,65 @@ class RoundEngine:
         from ..ops import _loader
         _loader.count_launch(n_native)               # our kernels inside the replayed graph
         self.last_client_losses = losses
+
+    # -- whole-round CUDA graph ------------------------------------------------------------
+    def all_rows_static(self) -> bool:
+        import os
+        if os.environ.get("BLADES_ROUND_GRAPH", "1") == "0":
+            return False
+        rows = list(range(len(self.local_idx)))
+        if not rows or not self.batchable_model or self.client_opt_spec not in ("SGD", None, torch.optim.SGD):
+            return False
+        return self._graph_eligible(rows) and all(
+            self._stock_for_batching(self.clients[self.local_idx[r]]) for r in rows)
+
+    def static_round(self, lr: float, aggregate_fn, matrix_fn) -> bool:
+        """Run one complete round through a captured CUDA graph.  The first two rounds with a given
+        (lr, server lr) run eagerly (they are real rounds and serve as warm-up); the third is captured and
+        replayed.  Returns False when the caller must run the round eagerly."""
+        rows = list(range(len(self.local_idx)))
+        key = (float(lr), float(self.server.current_lr()))
+        st = self._round_graphs.get(key)
+        if st is None:
+            if len(self._round_graphs) >= 2:           # bounded: each graph owns an activation pool
+                self._round_graphs.pop(next(iter(self._round_graphs)))
+            st = self._round_graphs[key] = {"seen": 0}
+        st["seen"] += 1
+        if st.get("disabled") or st["seen"] <= 2:
+            return False
+        from ..ops import _loader
+        if self.prestaged is not None:
+            X, y = self.prestaged
+        else:
+            X, y = self.stage_batches(rows, 1)
+        if "graph" not in st:
+            sx, sy = X.clone(), y.clone()
+            self._clamp_tensor(rows)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            before = _loader.LAUNCHES
+            try:
+                with torch.cuda.graph(graph):
+                    losses = self._batched_step(rows, lr, sx, sy)
+                    agg = aggregate_fn()
+                mat = matrix_fn()
+                ok = mat is not None and mat.step_applied
+            except Exception:
+                ok = False
+                torch.cuda.synchronize(self.device)
+            n_native = _loader.LAUNCHES - before
+            _loader.count_launch(-n_native)
+            if not ok:
+                st["disabled"] = True
+                return False
+            st.update(graph=graph, sx=sx, sy=sy, losses=losses, agg=agg, n_native=n_native)
+        st["sx"].copy_(X, non_blocking=True)
+        st["sy"].copy_(y, non_blocking=True)
+        st["graph"].replay()
+        _loader.count_launch(st["n_native"])
+        self.last_client_losses = st["losses"]
+        self.static_aggregate = st["agg"]
+        return True
 
     def _clamp_tensor(self, rows: List[int]) -> torch.Tensor:
         """Per-client loss clamps as a device tensor (cached: no H2D copy inside a graph capture)."""

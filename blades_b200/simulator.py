@@ -263,6 +263,13 @@ class Simulator(object):
         steps), attack callbacks, aggregation, server step."""
         eng = self.engine
         self.debug_logger.info(f"Train global round {global_round}")
+        if self._static_round_possible(num_rounds):
+            # whole round (train -> barrier -> fused attack+aggregate+server step -> barrier) as ONE CUDA
+            # graph replay: no per-round Python/launch overhead (matters most when G GPUs split the work)
+            virtual = self._cached_virtual()
+            if eng.static_round(lr, lambda: self._aggregate(virtual), lambda: self._last_matrix):
+                self.last_aggregate = eng.static_aggregate
+                return
         eng.timer.start("train")
         eng.train_local(num_rounds, lr)
         eng.timer.stop("train")
@@ -292,6 +299,26 @@ class Simulator(object):
             self.server.apply_update(aggregated)      # else: already done in the kernel epilogue
         eng.timer.stop("apply")
         eng.timer.flush()
+
+    def _cached_virtual(self):
+        key = tuple(id(cb) for cb in self.omniscient_callbacks)
+        if getattr(self, "_virt_key", None) != key:
+            self._virt_key = key
+            self._virt_val = self.engine.fusable_attack(self.omniscient_callbacks) if self._opts["fuse_attack"] else None
+        return self._virt_val
+
+    def _static_round_possible(self, local_steps: int) -> bool:
+        """The round is a fixed sequence of device work (no host decisions): fedsgd on the batched engine,
+        attack fused as virtual rows (or none), coordinate-wise built-in aggregator, fused SGD server step."""
+        from .aggregators import Mean, Median, Trimmedmean
+        eng = self.engine
+        if local_steps != 1 or eng.device.type != "cuda" or eng.timer.enabled or not self._opts["fuse_server_step"]:
+            return False
+        if type(self.aggregator) not in (Mean, Median, Trimmedmean) or not self.server._flat_fast_path_ok():
+            return False
+        if self.omniscient_callbacks and self._cached_virtual() is None:
+            return False
+        return eng.all_rows_static()
 
     def train_trainer(self, epoch, num_rounds, clients):
         """``mode='trainer'`` of the reference is non-functional (quirk Q1); it maps onto the

@@ -357,3 +357,27 @@ def test_wgrad_padded_rows():
     wgrad.grouped_wgrad(a_t.transpose(1, 2), b, out, 1.0)
     ref = a_t.double().transpose(1, 2) @ b.double()
     assert (out.double() - ref).abs().max() <= 2e-3 * ref.abs().max() + 1e-4
+
+
+@pytest.mark.parametrize("agg,attack", [("trimmedmean", "alie"), ("median", "ipm"), ("mean", None), ("trimmedmean", "labelflipping")])
+def test_whole_round_graph_equals_eager(agg, attack, tmp_path, monkeypatch):
+    """Rounds 3+ replay one captured CUDA graph (train + fused attack/aggregate/server step): same result as eager."""
+    from blades_b200 import Simulator
+    from blades_b200.datasets import synthetic_fldataset
+    from blades_b200.models import MLP
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("BLADES_ROUND_GRAPH", flag)
+        monkeypatch.setenv("BLADES_GRAPH", flag)
+        ds = synthetic_fldataset(10, shape=(28, 28), train_bs=8, seed=3, separation=2.0)
+        akw = {"num_clients": 10, "num_byzantine": 3} if attack == "alie" else None
+        sim = Simulator(ds, num_byzantine=3 if attack else 0, attack=attack, attack_kws=akw, aggregator=agg,
+                        aggregator_kws={"nb": 3} if agg == "trimmedmean" else None, use_cuda=True, seed=1,
+                        log_path=str(tmp_path / f"l{flag}"), progress=False)
+        torch.manual_seed(5)
+        m = MLP()
+        sim.run(m, global_rounds=6, local_steps=1, server_lr=1.0, client_lr=0.1, validate_interval=6)
+        if flag == "1":
+            assert any("graph" in st for st in sim.engine._round_graphs.values()), "round graph was not captured"
+        res.append(torch.cat([p.detach().cpu().reshape(-1) for p in m.parameters()]))
+    assert torch.allclose(res[0], res[1], atol=1e-5, rtol=1e-4), (res[0] - res[1]).abs().max()
