@@ -121,6 +121,10 @@ def run_ours(args) -> dict:
     model = build_model(model_name, classes)
     sim.prepare(model, "SGD", "SGD", "crossentropy", server_lr=1.0, client_lr=0.1)
     eng = sim.engine
+    if args.max_batched:
+        eng.max_batched_clients = args.max_batched
+    elif model_name == "resnet50":
+        eng.max_batched_clients = 64          # bound the activation footprint of the fused pass
     dev = eng.device
     clients = sim.get_clients()
 
@@ -217,6 +221,7 @@ def main():
     ap.add_argument("--clients", type=int, default=0, help="override the client count (debug)")
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--max-batched", type=int, default=0, help="clients per fused training pass (0 = all local)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":

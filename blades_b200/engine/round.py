@@ -116,6 +116,9 @@ class RoundEngine:
         self.last_client_losses: Optional[torch.Tensor] = None
         self.kernel_launches = 0
         self._clamps = {}
+        import os
+        #: clients per fused forward/backward (0 = all local clients at once)
+        self.max_batched_clients = int(os.environ.get("BLADES_MAX_BATCHED_CLIENTS", "0"))
         self._round_graphs = {}     # (client lr, server lr) -> captured whole-round graph state
         self.static_aggregate = None
         self._graphs = {}           # (rows, lr, shape) -> (CUDAGraph, static X, static y, losses)
@@ -180,7 +183,10 @@ class RoundEngine:
                 slice_rows.append(r)
         if batch_rows:
             try:
-                self._train_batched(batch_rows, lr)
+                # bound the activation footprint: at most ``max_batched_clients`` clients per fused pass
+                step = self.max_batched_clients or len(batch_rows)
+                for i in range(0, len(batch_rows), step):
+                    self._train_batched(batch_rows[i: i + step], lr)
             except cb.BatchedUnsupported:
                 slice_rows = sorted(slice_rows + batch_rows)
         for r in slice_rows:
@@ -212,6 +218,8 @@ class RoundEngine:
         replayed every round: the ~700 kernel launches of a ResNet-18 step cost one graph launch."""
         if self.prestaged is not None:           # device-resident inputs (kernel-only benchmarking)
             X, y = self.prestaged
+            if X.shape[0] != len(rows):
+                X, y = X[rows[0]: rows[-1] + 1], y[rows[0]: rows[-1] + 1]
         else:
             X, y = self.stage_batches(rows, 1)
         if not self._graph_eligible(rows):
@@ -254,6 +262,8 @@ class RoundEngine:
             return False
         rows = list(range(len(self.local_idx)))
         if not rows or not self.batchable_model or self.client_opt_spec not in ("SGD", None, torch.optim.SGD):
+            return False
+        if self.max_batched_clients and self.max_batched_clients < len(rows):
             return False
         return self._graph_eligible(rows) and all(
             self._stock_for_batching(self.clients[self.local_idx[r]]) for r in rows)

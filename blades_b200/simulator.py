@@ -275,14 +275,15 @@ class Simulator(object):
         eng.timer.stop("train")
 
         eng.timer.start("aggregate")
-        virtual = eng.fusable_attack(self.omniscient_callbacks) if self._opts["fuse_attack"] else None
-        if virtual is None and self.omniscient_callbacks:
+        callbacks = self._active_callbacks()
+        virtual = self._cached_virtual()
+        if virtual is None and callbacks:
             if self.world.distributed:
                 dense = eng.gather_dense()
                 for i, c in enumerate(self.get_clients()):
                     c._state["saved_update"] = dense[i]
                     c._slot = None
-            for cb in self.omniscient_callbacks:
+            for cb in callbacks:
                 cb(self)
             if self.world.distributed:
                 # write the (possibly modified) local rows back into the shard matrix
@@ -300,11 +301,18 @@ class Simulator(object):
         eng.timer.stop("apply")
         eng.timer.flush()
 
+    def _active_callbacks(self) -> List[Callable]:
+        """Registered omniscient callbacks minus the inherited no-op (label/sign flipping clients register
+        ``ByzantineClient.omniscient_callback``, which does nothing)."""
+        noop = ByzantineClient.omniscient_callback
+        return [cb for cb in self.omniscient_callbacks if getattr(cb, "__func__", None) is not noop]
+
     def _cached_virtual(self):
-        key = tuple(id(cb) for cb in self.omniscient_callbacks)
+        cbs = self._active_callbacks()
+        key = tuple(id(cb) for cb in cbs)
         if getattr(self, "_virt_key", None) != key:
             self._virt_key = key
-            self._virt_val = self.engine.fusable_attack(self.omniscient_callbacks) if self._opts["fuse_attack"] else None
+            self._virt_val = self.engine.fusable_attack(cbs) if (self._opts["fuse_attack"] and cbs) else None
         return self._virt_val
 
     def _static_round_possible(self, local_steps: int) -> bool:
@@ -316,7 +324,7 @@ class Simulator(object):
             return False
         if type(self.aggregator) not in (Mean, Median, Trimmedmean) or not self.server._flat_fast_path_ok():
             return False
-        if self.omniscient_callbacks and self._cached_virtual() is None:
+        if self._active_callbacks() and self._cached_virtual() is None:
             return False
         return eng.all_rows_static()
 
