@@ -56,7 +56,7 @@ def save_checkpoint(path: str, sim, server_sched=None, client_sched=None) -> Opt
                        "client": client_sched.state_dict() if client_sched else None},
         "rng": _rng_state(sim.device),
         "aggregator_state": agg.state_dict() if hasattr(agg, "state_dict") else {},
-        "data_cursors": sim.dataset.state_dict() if hasattr(sim.dataset, "state_dict") else {},
+        "data_cursors": sim.engine.data_cursors(),
         "config": {"n_clients": len(sim.get_clients()), "d": sim.engine.d,
                    "world_size": sim.world.size, "format_version": FORMAT_VERSION},
     }

@@ -40,20 +40,20 @@ class FLDataset:
         return self._test_dls[u_id]
 
     # ------------------------------------------------------------------ batched access
-    def get_train_batches(self, client_ids: Sequence[int], num_batches: int, pin: bool = True
+    def get_train_batches(self, client_ids: Sequence[int], num_batches: int, pin: bool = True, slot: int = 0
                           ) -> Tuple[torch.Tensor, torch.Tensor]:
         """Stack ``num_batches`` batches of each listed client:
         ``X[len(ids), k, B, ...]`` float32 and ``y[len(ids), k, B]`` int64, in reusable pinned memory.
         All clients must yield equal batch shapes (true for the built-in generators
         unless a client's shard is smaller than one batch)."""
-        fast = self._native_gather(client_ids, num_batches, pin)
+        fast = self._native_gather(client_ids, num_batches, pin, slot)
         if fast is not None:
             return fast
         rows = [self.get_train_data(c, num_batches) for c in client_ids]
         x0, y0 = rows[0][0]
         shape_x = (len(client_ids), num_batches) + tuple(x0.shape)
         shape_y = (len(client_ids), num_batches) + tuple(y0.shape)
-        key = (shape_x, shape_y)
+        key = (shape_x, shape_y, slot)          # ``slot``: independent staging buffers for double buffering
         buf = self._pinned.get(key)
         if buf is None:
             can_pin = pin and torch.cuda.is_available()
@@ -69,7 +69,7 @@ class FLDataset:
                 by[i, j].copy_(y)
         return bx, by
 
-    def _native_gather(self, client_ids, num_batches, pin):
+    def _native_gather(self, client_ids, num_batches, pin, slot=0):
         """Multi-threaded C++ batch assembly (csrc/host: bl_gather_batches) straight into the pinned
         staging buffer -- used when every stream is an untransformed float32 ``BatchStream``."""
         from .basedataset import BatchStream
@@ -98,7 +98,7 @@ class FLDataset:
                 idx[i, j * bs:(j + 1) * bs] = sl
         shape_x = (n, num_batches, bs) + tuple(shp)
         shape_y = (n, num_batches, bs)
-        key = (shape_x, shape_y)
+        key = (shape_x, shape_y, slot)
         buf = self._pinned.get(key)
         if buf is None:
             can_pin = pin and torch.cuda.is_available()

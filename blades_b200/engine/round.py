@@ -116,9 +116,17 @@ class RoundEngine:
         self.last_client_losses: Optional[torch.Tensor] = None
         self.kernel_launches = 0
         self._clamps = {}
+        self._pf_pool = None
+        self._pf_jobs = {}
+        self._pf_last = None
+        self._cursor_after = {}
+        self.track_cursors = False
         import os
+        self.prefetch = os.environ.get("BLADES_PREFETCH", "1") != "0"
         #: clients per fused forward/backward (0 = all local clients at once)
         self.max_batched_clients = int(os.environ.get("BLADES_MAX_BATCHED_CLIENTS", "0"))
+        self._sliced_graphs = {}
+        self._pending_batches = None
         self._round_graphs = {}     # (client lr, server lr) -> captured whole-round graph state
         self.static_aggregate = None
         self._graphs = {}           # (rows, lr, shape) -> (CUDAGraph, static X, static y, losses)
@@ -194,13 +202,69 @@ class RoundEngine:
 
     # -- batched fedsgd ------------------------------------------------------------
     def stage_batches(self, rows: Optional[Sequence[int]] = None, num_batches: int = 1):
-        """Host->device copy of the next round's inputs from pinned memory (async)."""
+        """This round's inputs on the device.  Host batch assembly (multi-threaded C++ gather into pinned
+        memory) and the H2D copy of round r+1 run on a worker thread + copy stream WHILE round r computes
+        (double-buffered pinned and device staging buffers, event-ordered); the reference does one blocking
+        ``.to(device)`` per batch per client inside the training loop (client.py:186)."""
         rows = list(range(len(self.local_idx))) if rows is None else list(rows)
-        ids = [self.clients[self.local_idx[r]].id() for r in rows]
-        X, y = self.dataset.get_train_batches(ids, num_batches)
+        if self.device.type != "cuda" or not self.prefetch:
+            X, y = self._assemble(rows, num_batches, 0)
+            self.h2d_bytes = X.numel() * X.element_size() + y.numel() * y.element_size()
+            nb = self.device.type == "cuda"
+            return X.to(self.device, non_blocking=nb), y.to(self.device, non_blocking=nb)
+        key = (tuple(rows), num_batches)
+        fut = self._pf_jobs.pop(key, None)
+        if fut is None:
+            fut = self._pf_submit(rows, num_batches)
+        X, y, ev, slot = fut.result()
+        torch.cuda.current_stream(self.device).wait_event(ev)
         self.h2d_bytes = X.numel() * X.element_size() + y.numel() * y.element_size()
-        nb = self.device.type == "cuda"
-        return X.to(self.device, non_blocking=nb), y.to(self.device, non_blocking=nb)
+        # consumers enqueue their reads right after this call; the slot may be refilled two rounds later
+        self._pf_last = (key, slot)
+        self._pf_jobs[key] = self._pf_submit(rows, num_batches)
+        return X, y
+
+    def _assemble(self, rows, num_batches, slot):
+        ids = [self.clients[self.local_idx[r]].id() for r in rows]
+        return self.dataset.get_train_batches(ids, num_batches, slot=slot)
+
+    def _pf_submit(self, rows, num_batches):
+        import concurrent.futures as cf
+        if self._pf_pool is None:
+            self._pf_pool = cf.ThreadPoolExecutor(max_workers=1, thread_name_prefix="blades-prefetch")
+            self._pf_stream = torch.cuda.Stream(device=self.device)
+            self._pf_dev = {}
+            self._pf_slot = 0
+        slot = self._pf_slot
+        self._pf_slot ^= 1
+        # the device staging buffer of this slot was last read by work enqueued on the main stream
+        consumed = torch.cuda.Event()
+        consumed.record(torch.cuda.current_stream(self.device))
+
+        def job():
+            torch.cuda.set_device(self.device)
+            X, y = self._assemble(rows, num_batches, slot)
+            if self.track_cursors:
+                self._cursor_after[slot] = self.dataset.state_dict()
+            bufs = self._pf_dev.get((slot, tuple(X.shape)))
+            if bufs is None:
+                bufs = self._pf_dev[(slot, tuple(X.shape))] = (
+                    torch.empty(X.shape, dtype=X.dtype, device=self.device),
+                    torch.empty(y.shape, dtype=y.dtype, device=self.device))
+            with torch.cuda.stream(self._pf_stream):
+                self._pf_stream.wait_event(consumed)
+                bufs[0].copy_(X, non_blocking=True)
+                bufs[1].copy_(y, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._pf_stream)
+            return bufs[0], bufs[1], ev, slot
+        return self._pf_pool.submit(job)
+
+    def data_cursors(self):
+        """Data-stream cursors as of the batches consumed so far (the prefetcher runs one round ahead)."""
+        if self._pf_last is not None and self.track_cursors and self._pf_last[1] in self._cursor_after:
+            return self._cursor_after[self._pf_last[1]]
+        return self.dataset.state_dict() if hasattr(self.dataset, "state_dict") else {}
 
     def _graph_eligible(self, rows: List[int]) -> bool:
         """CUDA-graph replay of the batched step needs every hook to be a pure device-tensor function:
@@ -369,7 +433,85 @@ class RoundEngine:
             c.optimizer = self.client_opt_spec(self.worker.parameters(), lr=lr)
         c.set_lr(lr)
 
+    # -- fedavg for stock clients: one captured CUDA graph per client visit ---------------------------
+    def _sliced_graph_key(self, c: BladesClient, local_steps: int, lr: float, shape):
+        return (type(c), float(getattr(c, "grad_sign", 1.0)), float(c.loss_clamp), getattr(c, "num_classes", None),
+                local_steps, float(lr), tuple(shape))
+
+    def _sliced_body(self, c: BladesClient, local_steps: int, lr: float, sx: torch.Tensor, sy: torch.Tensor,
+                     scratch: torch.Tensor) -> torch.Tensor:
+        """k local SGD steps of one client on the shared worker model, written as pure device work:
+        theta_w <- theta; k x (forward, clamp(CE), backward into the flat grad, theta_w -= lr*g);
+        scratch <- theta_w - theta.  Same math as reference client.py:178-193 + 127-131."""
+        w, g = self.wflat, self.gflat
+        with torch.no_grad():
+            w.theta.copy_(g.theta)
+            for (_, bw), (_, bg) in zip(self.worker.named_buffers(), self.server.get_model().named_buffers()):
+                bw.copy_(bg)
+        self.worker.train()
+        sign = float(getattr(c, "grad_sign", 1.0))
+        loss = None
+        for j in range(local_steps):
+            data, target = c.on_train_batch_begin(data=sx[j], target=sy[j])
+            w.grad.zero_()
+            out = self.worker(data)
+            loss = torch.clamp(torch.nn.functional.cross_entropy(out, target), 0, float(c.loss_clamp))
+            loss.backward()
+            with torch.no_grad():
+                w.theta.add_(w.grad, alpha=-lr * sign)
+        with torch.no_grad():
+            torch.sub(w.theta, g.theta, out=scratch)
+        return loss.detach()
+
+    def _train_sliced_graphed(self, r: int, local_steps: int, lr: float) -> bool:
+        """Graph-replayed time slice (stock clients, CUDA).  Returns False if the eager path must be used."""
+        import os
+        gi = self.local_idx[r]
+        c = self.clients[gi]
+        if self.device.type != "cuda" or os.environ.get("BLADES_GRAPH", "1") == "0":
+            return False
+        if not self._graph_eligible([r]) or not self._stock_for_batching(c) \
+                or self.client_opt_spec not in ("SGD", None, torch.optim.SGD):
+            return False
+        batches = self.dataset.get_train_data(c.id(), local_steps)
+        try:
+            X = torch.stack([b[0] for b in batches])
+            y = torch.stack([b[1] for b in batches])
+        except RuntimeError:
+            self._pending_batches = batches
+            return False
+        key = self._sliced_graph_key(c, local_steps, lr, X.shape)
+        st = self._sliced_graphs.get(key)
+        if st is None:
+            if self.wflat.grad is None:
+                self.wflat.attach_grad()
+            sx = torch.empty(X.shape, device=self.device, dtype=torch.float32)
+            sy = torch.empty(y.shape, device=self.device, dtype=torch.int64)
+            scratch = torch.empty(self.d, device=self.device, dtype=torch.float32)
+            sx.copy_(X)
+            sy.copy_(y)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._sliced_body(c, local_steps, lr, sx, sy, scratch)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                loss = self._sliced_body(c, local_steps, lr, sx, sy, scratch)
+            st = self._sliced_graphs[key] = (graph, sx, sy, scratch, loss)
+        graph, sx, sy, scratch, loss = st
+        sx.copy_(X, non_blocking=True)
+        sy.copy_(y, non_blocking=True)
+        graph.replay()
+        self.U[r].copy_(scratch)
+        c._state["saved_update"] = self.U[r]
+        return True
+
     def _train_timesliced(self, r: int, local_steps: int, lr: float) -> None:
+        self._pending_batches = None
+        if self._train_sliced_graphed(r, local_steps, lr):
+            return
         gi = self.local_idx[r]
         c = self.clients[gi]
         with torch.no_grad():
@@ -383,7 +525,8 @@ class RoundEngine:
             c.on_train_round_begin()
         else:
             self.worker.train()
-        data = self.dataset.get_train_data(c.id(), local_steps)
+        data = self._pending_batches if self._pending_batches is not None \
+            else self.dataset.get_train_data(c.id(), local_steps)
         c.local_training(data_batches=data)
         if custom_end:
             c.on_train_round_end()          # client computes/saves its own update (lands in U via bind_row)

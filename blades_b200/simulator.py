@@ -429,6 +429,7 @@ class Simulator(object):
         (device-synchronised, unlike the reference)."""
         self.prepare(model, server_optimizer, client_optimizer, loss, server_lr, client_lr,
                      reset_weights=resume is None)
+        self.engine.track_cursors = bool(checkpoint_path and checkpoint_interval)
         start_round = 1
         if resume is not None:
             from .checkpoint import load_checkpoint

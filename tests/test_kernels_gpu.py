@@ -381,3 +381,50 @@ def test_whole_round_graph_equals_eager(agg, attack, tmp_path, monkeypatch):
             assert any("graph" in st for st in sim.engine._round_graphs.values()), "round graph was not captured"
         res.append(torch.cat([p.detach().cpu().reshape(-1) for p in m.parameters()]))
     assert torch.allclose(res[0], res[1], atol=1e-5, rtol=1e-4), (res[0] - res[1]).abs().max()
+
+
+@pytest.mark.parametrize("attack", [None, "signflipping", "labelflipping"])
+def test_fedavg_graphed_slices_equal_eager(attack, tmp_path, monkeypatch):
+    """local_steps > 1: each client visit replays one captured graph; must match the eager per-client loop."""
+    from blades_b200 import Simulator
+    from blades_b200.datasets import synthetic_fldataset
+    from blades_b200.models import MLP
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("BLADES_GRAPH", flag)
+        ds = synthetic_fldataset(6, shape=(28, 28), train_bs=8, seed=3, separation=2.0)
+        sim = Simulator(ds, num_byzantine=2 if attack else 0, attack=attack, aggregator="median", use_cuda=True,
+                        seed=1, log_path=str(tmp_path / f"l{flag}"), progress=False)
+        torch.manual_seed(5)
+        m = MLP()
+        sim.run(m, global_rounds=3, local_steps=3, server_lr=1.0, client_lr=0.1, validate_interval=3)
+        if flag == "1":
+            assert sim.engine._sliced_graphs, "no time-slice graph was captured"
+        res.append(torch.cat([p.detach().cpu().reshape(-1) for p in m.parameters()]))
+    assert torch.allclose(res[0], res[1], atol=1e-5, rtol=1e-4), (res[0] - res[1]).abs().max()
+
+
+def test_gpu_checkpoint_resume_with_prefetch(tmp_path):
+    """The input prefetcher runs one round ahead; checkpoints must still resume bit-exactly."""
+    from blades_b200 import Simulator
+    from blades_b200.datasets import synthetic_fldataset
+    from blades_b200.models import MLP
+    ck = str(tmp_path / "ck.pt")
+
+    def make():
+        ds = synthetic_fldataset(6, shape=(28, 28), train_bs=8, train_per_client=24, seed=3, separation=2.0)
+        return Simulator(ds, num_byzantine=2, attack="alie", attack_kws={"num_clients": 6, "num_byzantine": 2},
+                         aggregator="trimmedmean", aggregator_kws={"nb": 2}, use_cuda=True, seed=1,
+                         log_path=str(tmp_path / "l"), progress=False)
+    torch.manual_seed(0)
+    m = MLP()
+    make().run(m, global_rounds=7, local_steps=1, server_lr=1.0, client_lr=0.1, validate_interval=7)
+    full = torch.cat([p.detach().cpu().reshape(-1) for p in m.parameters()])
+    torch.manual_seed(0)
+    ma = MLP()
+    make().run(ma, global_rounds=4, local_steps=1, server_lr=1.0, client_lr=0.1, validate_interval=4,
+               checkpoint_path=ck, checkpoint_interval=4)
+    mb = MLP()
+    make().run(mb, global_rounds=7, local_steps=1, server_lr=1.0, client_lr=0.1, validate_interval=7, resume=ck)
+    resumed = torch.cat([p.detach().cpu().reshape(-1) for p in mb.parameters()])
+    assert torch.allclose(resumed, full, atol=1e-6), (resumed - full).abs().max()
