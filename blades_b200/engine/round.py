@@ -126,7 +126,8 @@ class RoundEngine:
         #: clients per fused forward/backward (0 = all local clients at once)
         self.max_batched_clients = int(os.environ.get("BLADES_MAX_BATCHED_CLIENTS", "0"))
         self._sliced_graphs = {}
-        self._pending_batches = None
+        self._workers = []
+        self._slice_copied = {}
         self._round_graphs = {}     # (client lr, server lr) -> captured whole-round graph state
         self.static_aggregate = None
         self._graphs = {}           # (rows, lr, shape) -> (CUDAGraph, static X, static y, losses)
@@ -197,6 +198,8 @@ class RoundEngine:
                     self._train_batched(batch_rows[i: i + step], lr)
             except cb.BatchedUnsupported:
                 slice_rows = sorted(slice_rows + batch_rows)
+        if slice_rows:
+            slice_rows = self._train_sliced_graphed(slice_rows, local_steps, lr)
         for r in slice_rows:
             self._train_timesliced(r, local_steps, lr)
 
@@ -439,22 +442,23 @@ class RoundEngine:
                 local_steps, float(lr), tuple(shape))
 
     def _sliced_body(self, c: BladesClient, local_steps: int, lr: float, sx: torch.Tensor, sy: torch.Tensor,
-                     scratch: torch.Tensor) -> torch.Tensor:
+                     scratch: torch.Tensor, wk=None) -> torch.Tensor:
         """k local SGD steps of one client on the shared worker model, written as pure device work:
         theta_w <- theta; k x (forward, clamp(CE), backward into the flat grad, theta_w -= lr*g);
         scratch <- theta_w - theta.  Same math as reference client.py:178-193 + 127-131."""
-        w, g = self.wflat, self.gflat
+        worker, w = wk if wk is not None else (self.worker, self.wflat)
+        g = self.gflat
         with torch.no_grad():
             w.theta.copy_(g.theta)
-            for (_, bw), (_, bg) in zip(self.worker.named_buffers(), self.server.get_model().named_buffers()):
+            for (_, bw), (_, bg) in zip(worker.named_buffers(), self.server.get_model().named_buffers()):
                 bw.copy_(bg)
-        self.worker.train()
+        worker.train()
         sign = float(getattr(c, "grad_sign", 1.0))
         loss = None
         for j in range(local_steps):
             data, target = c.on_train_batch_begin(data=sx[j], target=sy[j])
             w.grad.zero_()
-            out = self.worker(data)
+            out = worker(data)
             loss = torch.clamp(torch.nn.functional.cross_entropy(out, target), 0, float(c.loss_clamp))
             loss.backward()
             with torch.no_grad():
@@ -463,55 +467,76 @@ class RoundEngine:
             torch.sub(w.theta, g.theta, out=scratch)
         return loss.detach()
 
-    def _train_sliced_graphed(self, r: int, local_steps: int, lr: float) -> bool:
-        """Graph-replayed time slice (stock clients, CUDA).  Returns False if the eager path must be used."""
+    def _slice_workers(self, k: int):
+        """k independent worker replicas (model + flat params + stream): client visits are tiny kernels, so
+        several clients run concurrently on separate streams to fill the 148 SMs."""
+        while len(self._workers) < k:
+            if not self._workers:
+                m, f = self.worker, self.wflat
+            else:
+                m = copy.deepcopy(self.worker)
+                f = FlatParams(m, device=self.device)
+            if f.grad is None:
+                f.attach_grad()
+            self._workers.append((m, f, torch.cuda.Stream(device=self.device)))
+        return self._workers[:k]
+
+    def _train_sliced_graphed(self, rows: List[int], local_steps: int, lr: float) -> List[int]:
+        """Graph-replayed time slices for the stock clients among ``rows`` (CUDA).  Returns the rows that
+        still need the eager path."""
         import os
-        gi = self.local_idx[r]
-        c = self.clients[gi]
-        if self.device.type != "cuda" or os.environ.get("BLADES_GRAPH", "1") == "0":
-            return False
-        if not self._graph_eligible([r]) or not self._stock_for_batching(c) \
+        if self.device.type != "cuda" or os.environ.get("BLADES_GRAPH", "1") == "0" \
                 or self.client_opt_spec not in ("SGD", None, torch.optim.SGD):
-            return False
-        batches = self.dataset.get_train_data(c.id(), local_steps)
-        try:
-            X = torch.stack([b[0] for b in batches])
-            y = torch.stack([b[1] for b in batches])
-        except RuntimeError:
-            self._pending_batches = batches
-            return False
-        key = self._sliced_graph_key(c, local_steps, lr, X.shape)
-        st = self._sliced_graphs.get(key)
-        if st is None:
-            if self.wflat.grad is None:
-                self.wflat.attach_grad()
-            sx = torch.empty(X.shape, device=self.device, dtype=torch.float32)
-            sy = torch.empty(y.shape, device=self.device, dtype=torch.int64)
-            scratch = torch.empty(self.d, device=self.device, dtype=torch.float32)
-            sx.copy_(X)
-            sy.copy_(y)
-            side = torch.cuda.Stream(device=self.device)
-            side.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(side):
-                for _ in range(2):
-                    self._sliced_body(c, local_steps, lr, sx, sy, scratch)
-            torch.cuda.current_stream(self.device).wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                loss = self._sliced_body(c, local_steps, lr, sx, sy, scratch)
-            st = self._sliced_graphs[key] = (graph, sx, sy, scratch, loss)
-        graph, sx, sy, scratch, loss = st
-        sx.copy_(X, non_blocking=True)
-        sy.copy_(y, non_blocking=True)
-        graph.replay()
-        self.U[r].copy_(scratch)
-        c._state["saved_update"] = self.U[r]
-        return True
+            return rows
+        todo = [r for r in rows if self._graph_eligible([r]) and self._stock_for_batching(self.clients[self.local_idx[r]])]
+        rest = [r for r in rows if r not in set(todo)]
+        if not todo:
+            return rest
+        n_streams = max(1, min(int(os.environ.get("BLADES_SLICE_STREAMS", "8")), len(todo)))
+        workers = self._slice_workers(n_streams)
+        main = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        for i, r in enumerate(todo):
+            wi = i % n_streams
+            model_w, flat_w, stream = workers[wi]
+            c = self.clients[self.local_idx[r]]
+            prev = self._slice_copied.get(wi)
+            if prev is not None:
+                prev.synchronize()                     # the pinned slot of this worker is free again
+            X, y = self.dataset.get_train_batches([c.id()], local_steps, slot=100 + wi)   # pinned [1,k,B,..]
+            X, y = X[0], y[0]
+            key = (wi,) + self._sliced_graph_key(c, local_steps, lr, X.shape)
+            st = self._sliced_graphs.get(key)
+            with torch.cuda.stream(stream):
+                stream.wait_event(ready)
+                if st is None:
+                    sx = torch.empty(X.shape, device=self.device, dtype=torch.float32)
+                    sy = torch.empty(y.shape, device=self.device, dtype=torch.int64)
+                    scratch = torch.empty(self.d, device=self.device, dtype=torch.float32)
+                    sx.copy_(X)
+                    sy.copy_(y)
+                    for _ in range(2):                       # warm-up on this stream
+                        self._sliced_body(c, local_steps, lr, sx, sy, scratch, (model_w, flat_w))
+                    stream.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, stream=stream):
+                        loss = self._sliced_body(c, local_steps, lr, sx, sy, scratch, (model_w, flat_w))
+                    st = self._sliced_graphs[key] = (graph, sx, sy, scratch, loss)
+                graph, sx, sy, scratch, loss = st
+                sx.copy_(X, non_blocking=True)
+                sy.copy_(y, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                self._slice_copied[wi] = ev
+                graph.replay()
+                self.U[r].copy_(scratch)
+            c._state["saved_update"] = self.U[r]
+        for _, _, stream in workers:
+            main.wait_stream(stream)
+        return rest
 
     def _train_timesliced(self, r: int, local_steps: int, lr: float) -> None:
-        self._pending_batches = None
-        if self._train_sliced_graphed(r, local_steps, lr):
-            return
         gi = self.local_idx[r]
         c = self.clients[gi]
         with torch.no_grad():
@@ -525,8 +550,7 @@ class RoundEngine:
             c.on_train_round_begin()
         else:
             self.worker.train()
-        data = self._pending_batches if self._pending_batches is not None \
-            else self.dataset.get_train_data(c.id(), local_steps)
+        data = self.dataset.get_train_data(c.id(), local_steps)
         c.local_training(data_batches=data)
         if custom_end:
             c.on_train_round_end()          # client computes/saves its own update (lands in U via bind_row)
