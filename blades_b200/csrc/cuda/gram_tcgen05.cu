@@ -38,7 +38,9 @@ struct GramParams {
     int mb_per_cta;
     int stages;
     int split3;                          // 1 = 3xTF32
-    int slabs;                           // 128 B column slabs per stage (K chunk = 32*slabs floats per row)
+    int slabs;                           // column slabs per stage (K chunk = slabs * row_bytes/4 floats per row)
+    int row_bytes;                       // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B: halves the stage so that 3xTF32
+                                         // staging of up to 512 rows still gets a 3-deep pipeline)
     long long chunk0, chunk1;            // K chunk range of this launch
     float* gram;                         // [tile_rows][ld_gram] fp32, accumulated with red.add
     int ld_gram;
@@ -52,7 +54,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages][hi tile][lo tile?] then barriers
-    const uint32_t slab_bytes = (uint32_t)p.tile_rows * 128u;            // one [tile_rows x 128 B] SW128 tile
+    const uint32_t rb = (uint32_t)p.row_bytes;
+    const uint32_t slab_bytes = (uint32_t)p.tile_rows * rb;              // one [tile_rows x row_bytes] swizzled tile
     const uint32_t tile_bytes = slab_bytes * (uint32_t)p.slabs;          // hi (or lo) part of a stage
     const uint32_t stage_bytes = tile_bytes * (p.split3 ? 2u : 1u);
     uint8_t* tiles = smem_raw;                       // dynamic smem base is 1024-aligned (checked on host)
@@ -93,7 +96,7 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
     if (warp == 1) bl::tmem_alloc_dyn(tmem_slot, tmem_cols);
     // rows of the tile that no TMA box covers must read as zero (hi and lo tiles, every stage)
     if (p.rows_covered < p.tile_rows) {
-        const uint32_t beg = (uint32_t)p.rows_covered * 128u;
+        const uint32_t beg = (uint32_t)p.rows_covered * rb;
         const int n_tiles = p.stages * (p.split3 ? 2 : 1) * p.slabs;     // consecutive slabs
         for (int t = 0; t < n_tiles; ++t) {
             uint8_t* base = tiles + (size_t)t * slab_bytes;
@@ -111,18 +114,19 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
         if (warp == 0) {
             // ================= TMA producer =================
             if (lane == 0) {
-                const uint32_t tx = (uint32_t)p.rows_covered * 128u * (uint32_t)p.slabs;
+                const uint32_t tx = (uint32_t)p.rows_covered * rb * (uint32_t)p.slabs;
                 for (int it = 0; it < iters; ++it) {
                     const int s = it % p.stages;
                     const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
                     bl::mbar_wait(&empty[s], ph ^ 1u);
                     bl::mbar_arrive_expect_tx(&full[s], tx);
                     uint8_t* dst = tiles + (size_t)s * stage_bytes;
-                    const int c0 = (int)((kc0 + it) * GRAM_CHUNK * p.slabs);
+                    const int cf = p.row_bytes / 4;             // floats per slab row
+                    const int c0 = (int)((kc0 + it) * cf * p.slabs);
                     for (int sl = 0; sl < p.slabs; ++sl)
                         for (int b = 0; b < p.n_blocks; ++b)
-                            bl::tma_load_2d(dst + (size_t)sl * slab_bytes + (size_t)p.blk_smem_row[b] * 128u,
-                                            &p.maps[b], &full[s], c0 + sl * GRAM_CHUNK, 0);
+                            bl::tma_load_2d(dst + (size_t)sl * slab_bytes + (size_t)p.blk_smem_row[b] * rb,
+                                            &p.maps[b], &full[s], c0 + sl * cf, 0);
                 }
             }
         } else if (warp == 1) {
@@ -139,21 +143,22 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
                     const uint32_t hi = hi0 + (uint32_t)sl * slab_bytes;
                     const uint32_t lo = hi + tile_bytes;
                     for (int m = 0; m < nmb; ++m) {
-                        const uint32_t a_off = (uint32_t)(mb0 + m) * 128u * 128u;
+                        const uint32_t a_off = (uint32_t)(mb0 + m) * 128u * rb;
                         for (int h = 0; h < n_halves; ++h) {
                             const int ncols = min(256, p.np_n - h * 256);
                             const uint32_t idesc = bl::umma_idesc_tf32(128, (uint32_t)ncols, 0, 0);
-                            const uint32_t b_off = (uint32_t)h * 256u * 128u;
+                            const uint32_t b_off = (uint32_t)h * 256u * rb;
                             const uint32_t d_tmem = tmem_base + (uint32_t)(m * p.np_n + h * 256);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {          // 4 x (K = 8 tf32 = 32 B) per 128 B row
+                            const uint32_t sbo = 8u * rb;            // 8-row swizzle atom
+                            const uint32_t lay = (rb == 128u) ? bl::kLayoutSw128 : bl::kLayoutSw64;
+                            for (int k = 0; k < (int)(rb / 32u); ++k) {   // K = 8 tf32 = 32 B per MMA
                                 const uint32_t koff = (uint32_t)k * 32u;
-                                const uint64_t a_hi = bl::umma_smem_desc(hi + a_off + koff, 16, 1024);
-                                const uint64_t b_hi = bl::umma_smem_desc(hi + b_off + koff, 16, 1024);
+                                const uint64_t a_hi = bl::umma_smem_desc(hi + a_off + koff, 16, sbo, lay);
+                                const uint64_t b_hi = bl::umma_smem_desc(hi + b_off + koff, 16, sbo, lay);
                                 bl::umma_tf32(d_tmem, a_hi, b_hi, idesc, (it > 0 || sl > 0 || k > 0) ? 1u : 0u);
                                 if (p.split3) {
-                                    const uint64_t a_lo = bl::umma_smem_desc(lo + a_off + koff, 16, 1024);
-                                    const uint64_t b_lo = bl::umma_smem_desc(lo + b_off + koff, 16, 1024);
+                                    const uint64_t a_lo = bl::umma_smem_desc(lo + a_off + koff, 16, sbo, lay);
+                                    const uint64_t b_lo = bl::umma_smem_desc(lo + b_off + koff, 16, sbo, lay);
                                     bl::umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
                                     bl::umma_tf32(d_tmem, a_lo, b_hi, idesc, 1u);
                                 }
@@ -169,7 +174,7 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
         } else {
             // ================= converter (warps 2..5) =================
             const int ct = threadIdx.x - 64;                       // 0..127
-            const uint32_t n16 = (uint32_t)p.rows_covered * 8u;    // 16 B granules in the covered part of a slab
+            const uint32_t n16 = (uint32_t)p.rows_covered * (rb / 16u);   // 16 B granules in the covered part of a slab
             for (int it = 0; it < iters; ++it) {
                 const int s = it % p.stages;
                 const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
@@ -236,7 +241,6 @@ extern "C" int bl_gram_tcgen05(const GramBlockDesc* blocks, int n_blocks, long l
                                long long col1, float* gram, int ld_gram, int split3, int num_sms,
                                void* stream) {
     if (n_blocks < 1 || n_blocks > GRAM_MAX_BLOCKS) return -1;
-    if (col0 % GRAM_CHUNK != 0) return -2;
     GramParams p;
     memset(&p, 0, sizeof(p));
     p.n_blocks = n_blocks;
@@ -248,11 +252,6 @@ extern "C" int bl_gram_tcgen05(const GramBlockDesc* blocks, int n_blocks, long l
         p.blk_rows_pad[b] = pad;
         p.blk_smem_row[b] = row;
         row += pad;
-        uint64_t dims[2] = {(uint64_t)d, (uint64_t)blocks[b].rows};
-        uint64_t strides[1] = {(uint64_t)blocks[b].ld * 4};
-        uint32_t box[2] = {GRAM_CHUNK, (uint32_t)pad};
-        int r = bl::make_tmap_f32(&p.maps[b], blocks[b].base, 2, dims, strides, box);
-        if (r != 0) return 1000 + r;
     }
     p.rows_covered = row;
     if (row > 512) return -5;
@@ -268,22 +267,33 @@ extern "C" int bl_gram_tcgen05(const GramBlockDesc* blocks, int n_blocks, long l
     const int groups = (p.n_mblk + p.mb_per_cta - 1) / p.mb_per_cta;
     p.split3 = split3 ? 1 : 0;
     const size_t budget = 227 * 1024 - 1024 - 256;
+    // 128 B rows unless the (hi + lo) staging of one stage would leave fewer than 2 pipeline stages
+    p.row_bytes = 128;
+    if ((size_t)p.tile_rows * 128 * (p.split3 ? 2 : 1) * 2 > budget) p.row_bytes = 64;
+    for (int b = 0; b < n_blocks; ++b) {
+        uint64_t dims[2] = {(uint64_t)d, (uint64_t)blocks[b].rows};
+        uint64_t strides[1] = {(uint64_t)blocks[b].ld * 4};
+        uint32_t box[2] = {(uint32_t)p.row_bytes / 4, (uint32_t)p.blk_rows_pad[b]};
+        int r = bl::make_tmap_f32(&p.maps[b], blocks[b].base, 2, dims, strides, box,
+                                  p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+        if (r != 0) return 1000 + r;
+    }
     // wider K chunks per row (2 x 128 B) = longer DRAM bursts per row visit and half the barrier round trips
     // per byte (measured: N=100 tf32 1.85 -> 1.55 ms, 3xTF32 2.41 -> 1.93 ms; 4 slabs gave nothing more);
     // needs at least 3 pipeline stages to pay off
     int slabs = 2;
-    if ((size_t)p.tile_rows * 128 * slabs * (p.split3 ? 2 : 1) * 3 > budget) slabs = 1;
+    if ((size_t)p.tile_rows * p.row_bytes * slabs * (p.split3 ? 2 : 1) * 3 > budget) slabs = 1;
     {
         const char* e = getenv("BLADES_GRAM_SLABS");
         if (e) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) slabs = v; }
     }
     p.slabs = slabs;
-    const size_t stage_bytes = (size_t)p.tile_rows * 128 * slabs * (p.split3 ? 2 : 1);
+    const size_t stage_bytes = (size_t)p.tile_rows * p.row_bytes * slabs * (p.split3 ? 2 : 1);
     int stages = (int)(budget / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) return -7;
     p.stages = stages;
-    const long long chunk = (long long)GRAM_CHUNK * slabs;
+    const long long chunk = (long long)(p.row_bytes / 4) * slabs;
     if (col0 % chunk != 0) return -2;
     p.chunk0 = col0 / chunk;
     p.chunk1 = (col1 + chunk - 1) / chunk;

@@ -131,6 +131,7 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
 //   contiguous along M/N, 32 B chunks XOR-swizzled with (k row & 3), K atoms of 4 rows (512 B) -- what
 //   TMA produces with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  SBO = stride between 4-row K atoms.
 constexpr uint32_t kLayoutSw128 = 2;
+constexpr uint32_t kLayoutSw64 = 4;          // rows of 64 B, 8-row atoms of 512 B
 constexpr uint32_t kLayoutSw128Base32B = 1;
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                                    uint32_t layout_type = kLayoutSw128) {

@@ -51,6 +51,7 @@ class PhaseTimer:
         if not self.enabled:
             return
         if self.cuda:
+            torch.cuda.nvtx.range_push(name)
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             self._cur[name] = (ev, None)
@@ -64,6 +65,7 @@ class PhaseTimer:
         if self.cuda:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
+            torch.cuda.nvtx.range_pop()
             self._cur[name] = (beg, ev)
         else:
             self._cur[name] = (beg, time.perf_counter())

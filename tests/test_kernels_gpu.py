@@ -134,8 +134,11 @@ def test_gram(n, d):
     from blades_b200.ops import gram
     U = torch.randn(n, d, device=_dev()) * 0.01 + 0.003
     ref = (U.double() @ U.double().T).cpu().numpy()
+    from blades_b200.ops import _loader
     for prec in ("tf32x3", "tf32"):
+        before = _loader.LAUNCHES
         G = gram.gram(U, precision=prec)
+        assert _loader.LAUNCHES > before, f"tcgen05 Gram kernel did not run for n={n} {prec}"
         tol = 1e-5 if prec == "tf32x3" else 2e-3
         scale = np.abs(ref).max()
         assert np.abs(G - ref).max() <= tol * scale, (prec, np.abs(G - ref).max() / scale)
