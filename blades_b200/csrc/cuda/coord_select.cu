@@ -10,6 +10,7 @@
 // with multiplicity f -- f identical malicious rows are never stored or sorted.
 // The result is written to every replica and theta += lr*agg is applied in the same kernel.
 #include "common.cuh"
+#include <cstdlib>
 
 #define CE(a, b) { float lo_ = fminf(v[a], v[b]); v[b] = fmaxf(v[a], v[b]); v[a] = lo_; }
 #include "gen/sortnet_gen.cuh"
@@ -31,8 +32,14 @@ struct SelectParams {
 // Pipe balance (ncu: the ALU pipe -- FMNMX/ISETP/SEL, 16 lanes/clk/SMSP -- is the limiter): the sorting
 // network has to live on the ALU pipe, so everything else is written as FFMA / FADD.SAT arithmetic for
 // the otherwise idle FMA pipe: masks are 0/1 floats, rank tests are saturating adds.
-template <int NP>
-__global__ void __launch_bounds__(128)
+// Block size: the straight-line network is ~30-50 KB of SASS, more than the 32 KB L1.5 instruction cache, and ncu
+// showed "no_instruction" as the top stall with 128-thread blocks (20 independent warps per SM each streaming
+// the code at a different position).  Large blocks keep the warps of an SM roughly in lockstep so they share
+// instruction-cache lines; two resident blocks per SM still overlap one block's load phase with the other's sort.
+template <int NP> struct SelectBlock { static constexpr int kMax = NP <= 80 ? 640 : (NP <= 104 ? 512 : 384); };
+
+template <int NP, int MODE>
+__global__ void __launch_bounds__(SelectBlock<NP>::kMax)
 coord_select_kernel(const __grid_constant__ SelectParams p) {
     const long long c = p.c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= p.c1) return;
@@ -40,8 +47,10 @@ coord_select_kernel(const __grid_constant__ SelectParams p) {
     const int n = p.n_real;
     // Issue ALL row loads back to back before the first use (rows[i >= n] alias row 0 on the host
     // side, so no load is predicated): one DRAM/NVLink round trip per thread instead of NP.
+    // 32-bit element offset from the (uniform) row base: no per-load 64-bit address arithmetic on the ALU pipe.
+    const unsigned cu = (unsigned)c;
 #pragma unroll
-    for (int i = 0; i < NP; ++i) v[i] = bl_ldg_stream(p.rows[i] + c);
+    for (int i = 0; i < NP; ++i) v[i] = __ldcs(p.rows[i] + cu);      // ld.global.cs: streaming, evict-first
 #pragma unroll
     for (int i = 0; i < NP; ++i) v[i] = bl_sanitize(v[i]);
 
@@ -66,9 +75,10 @@ coord_select_kernel(const __grid_constant__ SelectParams p) {
             m = -p.virt_param * mu;
         }
     }
-    // padding slots sort to the top: FLT_MAX (finite, so 0-weight products stay 0)
+    // padding slots sort to the top: FLT_MAX (finite, so 0-weight products stay 0); n > NP - 8 by dispatch,
+    // so only the last 7 slots can be padding
 #pragma unroll
-    for (int i = 0; i < NP; ++i) v[i] = (i < n) ? v[i] : FLT_MAX;
+    for (int i = (NP >= 8 ? NP - 7 : 0); i < NP; ++i) v[i] = (i < n) ? v[i] : FLT_MAX;
 
     SortNet<NP>::run(v);
 
@@ -82,7 +92,7 @@ coord_select_kernel(const __grid_constant__ SelectParams p) {
     }
     const float ff = (float)f;
     float agg;
-    if (p.mode == 0) {
+    if (MODE == 0) {
         const float lo = (float)p.trim_b, hi = (float)(N - p.trim_b);   // keep merged ranks [lo, hi)
         float s = 0.f;
 #pragma unroll
@@ -183,12 +193,26 @@ coord_select_large_kernel(const __grid_constant__ SelectLargeParams p) {
     }
 }
 
+static int select_block_size(int kmax) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("BLADES_SELECT_BLOCK");
+        forced = e ? atoi(e) : 0;
+    }
+    int b = forced > 0 ? forced : 320;
+    if (b > kmax) b = kmax;
+    return (b / 32) * 32;
+}
+
 template <int NP>
 static cudaError_t launch_small(const SelectParams& p, cudaStream_t st) {
     const long long cols = p.c1 - p.c0;
     if (cols <= 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((cols + 127) / 128);
-    coord_select_kernel<NP><<<grid, 128, 0, st>>>(p);
+    if (p.c1 > 0xFFFFFFFFLL) return cudaErrorInvalidValue;      // 32-bit element offsets
+    const int block = select_block_size(SelectBlock<NP>::kMax);
+    const unsigned grid = (unsigned)((cols + block - 1) / block);
+    if (p.mode == 0) coord_select_kernel<NP, 0><<<grid, block, 0, st>>>(p);
+    else coord_select_kernel<NP, 1><<<grid, block, 0, st>>>(p);
     return cudaGetLastError();
 }
 
