@@ -199,7 +199,7 @@ static int select_block_size(int kmax) {
         const char* e = getenv("BLADES_SELECT_BLOCK");
         forced = e ? atoi(e) : 0;
     }
-    int b = forced > 0 ? forced : 320;
+    int b = forced > 0 ? forced : 256;       // measured best of {128, 256, 320, 640}
     if (b > kmax) b = kmax;
     return (b / 32) * 32;
 }

@@ -13,7 +13,8 @@
 //     different GPUs: one TMA descriptor per block (peer memory is TMA-addressable through the
 //     NVLink mapping); SWIZZLE_128B, K-major; out-of-range rows/columns are zero-filled by TMA.
 //   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread issues
-//     tcgen05.mma.kind::tf32), warps 2-5 = converter + epilogue.  The converter sanitises NaN/inf
+//     tcgen05.mma.kind::tf32), warps 2-9 = converter (ncu showed the 4-warp converter, not HBM or the tensor
+//     pipe, pacing the pipeline), warps 2-5 also run the epilogue.  The converter sanitises NaN/inf
 //     (nan_to_num) and, for 3xTF32, splits x = hi + lo (hi = tf32-truncated) into two smem tiles so
 //     that  hi*hi + hi*lo + lo*hi  recovers ~fp32 accuracy (distances suffer cancellation).
 //   * pipeline: full[s] (TMA -> converter), ready[s] (converter -> MMA), empty[s] (tcgen05.commit ->
@@ -48,7 +49,8 @@ struct GramParams {
 
 namespace {
 
-constexpr int kThreads = 192;            // 6 warps
+constexpr int kThreads = 320;            // 10 warps: TMA, MMA, 8 converter (4 of them also epilogue)
+constexpr int kConvThreads = 256;
 
 __global__ void __launch_bounds__(kThreads, 1)
 gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
@@ -87,7 +89,7 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
         for (int b = 0; b < p.n_blocks; ++b) bl::tma_prefetch_desc(&p.maps[b]);
         for (int s = 0; s < p.stages; ++s) {
             bl::mbar_init(&full[s], 1);
-            bl::mbar_init(&ready[s], 4);     // one arrive per converter warp
+            bl::mbar_init(&ready[s], kConvThreads / 32);     // one arrive per converter warp
             bl::mbar_init(&empty[s], 1);
         }
         bl::mbar_init(done, 1);
@@ -173,7 +175,7 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
             }
         } else {
             // ================= converter (warps 2..5) =================
-            const int ct = threadIdx.x - 64;                       // 0..127
+            const int ct = threadIdx.x - 64;                       // 0..255
             const uint32_t n16 = (uint32_t)p.rows_covered * (rb / 16u);   // 16 B granules in the covered part of a slab
             for (int it = 0; it < iters; ++it) {
                 const int s = it % p.stages;
@@ -182,7 +184,8 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
                 for (int sl = 0; sl < p.slabs; ++sl) {
                 uint8_t* hi = tiles + (size_t)s * stage_bytes + (size_t)sl * slab_bytes;
                 uint8_t* lo = hi + tile_bytes;
-                for (uint32_t g = ct; g < n16; g += 128) {
+#pragma unroll 4
+                for (uint32_t g = ct; g < n16; g += kConvThreads) {
                     float4 x = *reinterpret_cast<float4*>(hi + g * 16u);
                     x.x = bl_sanitize(x.x); x.y = bl_sanitize(x.y); x.z = bl_sanitize(x.z); x.w = bl_sanitize(x.w);
                     float4 h;
@@ -203,7 +206,7 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
         }
 
         // ================= epilogue (warps 2..5): TMEM -> red.global.add =================
-        if (warp >= 2) {
+        if (warp >= 2 && warp < 6) {
             bl::mbar_wait(done, 0);
             bl::tc_fence_after();
             const int q = warp & 3;                                // TMEM lane quarter of this warp

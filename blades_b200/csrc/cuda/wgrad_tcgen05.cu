@@ -12,7 +12,7 @@
 //            (the only smem layout tcgen05 accepts for MN-major tf32 operands)
 //   warp 1   MMA issuer: tcgen05.mma.kind::tf32, M=128, N=BN, one K=8 atom per instruction,
 //            accumulators double-buffered in TMEM (2 x 256 columns)
-//   warps 2-5 epilogue: tcgen05.ld -> scale/sanitise -> 128 B-per-thread global stores
+//   warps 2-9 epilogue (two per TMEM lane quarter): tcgen05.ld -> scale/sanitise -> smem transpose -> coalesced stores
 // Persistent CTAs walk (client, m-tile, n-tile) tiles round-robin; smem and TMEM pipelines run
 // across tile boundaries so the next tile's loads/MMAs overlap the current tile's stores.
 #include "common.cuh"
@@ -36,7 +36,7 @@ struct WgradParams {
 };
 
 namespace {
-constexpr int kWThreads = 192;
+constexpr int kWThreads = 320;           // TMA, MMA + 8 epilogue warps (2 per TMEM lane quarter)
 constexpr int kEpiLd = 36;               // padded row (floats): 16 B aligned, conflict-free float4 access
 
 __global__ void __launch_bounds__(kWThreads, 1)
@@ -63,7 +63,7 @@ wgrad_tcgen05_kernel(const __grid_constant__ WgradParams p) {
         bl::tma_prefetch_desc(&p.map_a);
         bl::tma_prefetch_desc(&p.map_b);
         for (int s = 0; s < p.stages; ++s) { bl::mbar_init(&full[s], 1); bl::mbar_init(&empty[s], 1); }
-        for (int i = 0; i < 2; ++i) { bl::mbar_init(&tfull[i], 1); bl::mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < 2; ++i) { bl::mbar_init(&tfull[i], 1); bl::mbar_init(&tempty[i], 8); }
         bl::fence_barrier_init();
     }
     if (warp == 1) bl::tmem_alloc<512>(tmem_slot);
@@ -130,7 +130,8 @@ wgrad_tcgen05_kernel(const __grid_constant__ WgradParams p) {
         }
     } else {
         // ================= epilogue =================
-        const int q = warp & 3;
+        const int q = warp & 3;                  // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;        // the two warps of a quarter split the column chunks
         uint32_t tcount = 0;
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
             const int nt = (int)(tile % p.n_tiles);
@@ -145,7 +146,7 @@ wgrad_tcgen05_kernel(const __grid_constant__ WgradParams p) {
             float* stg = epi + (warp - 2) * (32 * kEpiLd);
             const int rsub = lane >> 3, csub = (lane & 7) * 4;
             float* obase = p.out + (long long)c * p.batch_stride;
-            for (int cb = 0; cb < p.BN; cb += 32) {
+            for (int cb = half * 32; cb < p.BN; cb += 64) {
                 float v[32];
                 bl::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u + (uint32_t)cb, v);
                 const int n0 = nt * p.BN + cb;
@@ -225,11 +226,11 @@ extern "C" int bl_grouped_wgrad(const float* a, const float* b, float* out, int 
         if (r != 0) return 1000 + r;
     }
     const size_t stage_bytes = (size_t)(4 + bn / 32) * p.KT * 128;
-    int stages = (int)((190 * 1024) / stage_bytes);
+    int stages = (int)((180 * 1024) / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) return -2;
     p.stages = stages;
-    const size_t smem = stages * stage_bytes + 256 + 4 * 32 * kEpiLd * sizeof(float);
+    const size_t smem = stages * stage_bytes + 256 + 8 * 32 * kEpiLd * sizeof(float);
     static bool attr_done = false;       // opt in to the full 227 KB once (not a stream op: keep it out of graph capture)
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
