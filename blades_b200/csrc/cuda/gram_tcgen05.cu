@@ -40,6 +40,7 @@ struct GramParams {
     int stages;
     int split3;                          // 1 = 3xTF32
     int slabs;                           // column slabs per stage (K chunk = slabs * row_bytes/4 floats per row)
+    int dbg;                             // debug bisect: 1 = converter does nothing, 2 = no MMA issue
     int row_bytes;                       // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B: halves the stage so that 3xTF32
                                          // staging of up to 512 rows still gets a 3-deep pipeline)
     long long chunk0, chunk1;            // K chunk range of this launch
@@ -72,14 +73,16 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
     const int lane = threadIdx.x & 31;
 
     // ---- work assignment
+    // K chunks are dealt round-robin (chunk = chunk0 + blockIdx.x + it * gridDim.x): at any moment the 148 CTAs
+    // read one contiguous ~37 KB window of every row, so DRAM pages are shared between neighbouring CTAs.
+    // (A blocked split -- each CTA walking its own far-apart K range -- topped out at 61 % of the copy
+    // bandwidth even with the MMA and converter disabled: 148 x 100 independent 256 B streams.)
     const int ksplits = gridDim.x;
     const long long nchunks = p.chunk1 - p.chunk0;
-    const long long per = (nchunks + ksplits - 1) / ksplits;
-    const long long kc0 = p.chunk0 + per * blockIdx.x;
-    const long long kc1 = min(p.chunk1, kc0 + per);
+    const long long kc0 = p.chunk0 + blockIdx.x;
     const int mb0 = blockIdx.y * p.mb_per_cta;
     const int nmb = min(p.mb_per_cta, p.n_mblk - mb0);
-    const int iters = (int)max(0LL, kc1 - kc0);
+    const int iters = (int)((nchunks > (long long)blockIdx.x) ? (nchunks - blockIdx.x + ksplits - 1) / ksplits : 0);
     const uint32_t tmem_cols_needed = (uint32_t)(p.mb_per_cta * p.np_n);
     uint32_t tmem_cols = 32;
     while (tmem_cols < tmem_cols_needed) tmem_cols <<= 1;
@@ -124,7 +127,7 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
                     bl::mbar_arrive_expect_tx(&full[s], tx);
                     uint8_t* dst = tiles + (size_t)s * stage_bytes;
                     const int cf = p.row_bytes / 4;             // floats per slab row
-                    const int c0 = (int)((kc0 + it) * cf * p.slabs);
+                    const int c0 = (int)((kc0 + (long long)it * ksplits) * cf * p.slabs);
                     for (int sl = 0; sl < p.slabs; ++sl)
                         for (int b = 0; b < p.n_blocks; ++b)
                             bl::tma_load_2d(dst + (size_t)sl * slab_bytes + (size_t)p.blk_smem_row[b] * rb,
@@ -141,7 +144,7 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
                 bl::tc_fence_after();
                 if (lane == 0) {
                     const uint32_t hi0 = bl::smem_u32(tiles + (size_t)s * stage_bytes);
-                    for (int sl = 0; sl < p.slabs; ++sl) {
+                    for (int sl = 0; sl < ((p.dbg & 2) ? 0 : p.slabs); ++sl) {
                     const uint32_t hi = hi0 + (uint32_t)sl * slab_bytes;
                     const uint32_t lo = hi + tile_bytes;
                     for (int m = 0; m < nmb; ++m) {
@@ -181,7 +184,7 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
                 const int s = it % p.stages;
                 const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
                 bl::mbar_wait(&full[s], ph);
-                for (int sl = 0; sl < p.slabs; ++sl) {
+                for (int sl = 0; sl < ((p.dbg & 1) ? 0 : p.slabs); ++sl) {
                 uint8_t* hi = tiles + (size_t)s * stage_bytes + (size_t)sl * slab_bytes;
                 uint8_t* lo = hi + tile_bytes;
 #pragma unroll 4
@@ -291,6 +294,10 @@ extern "C" int bl_gram_tcgen05(const GramBlockDesc* blocks, int n_blocks, long l
         if (e) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) slabs = v; }
     }
     p.slabs = slabs;
+    {
+        const char* e = getenv("BLADES_GRAM_DBG");
+        p.dbg = e ? atoi(e) : 0;
+    }
     const size_t stage_bytes = (size_t)p.tile_rows * p.row_bytes * slabs * (p.split3 ? 2 : 1);
     int stages = (int)(budget / stage_bytes);
     if (stages > 8) stages = 8;
