@@ -32,7 +32,6 @@ struct WgradParams {
     float* out;              // out[c*batch_stride + m*N + n]
     long long batch_stride;
     int vec_ok;              // 16 B aligned stores possible
-    int dbg_swap;            // debug: swap LBO/SBO in the operand descriptors
 };
 
 namespace {
@@ -117,7 +116,7 @@ wgrad_tcgen05_kernel(const __grid_constant__ WgradParams p) {
                     for (int ka = 0; ka < p.KT / 8; ++ka) {    // one 8-row K atom (1024 B) per MMA
                         // MN-major tf32: SWIZZLE_128B_BASE32B; LBO = stride between 32-float column
                         // blocks, SBO = stride between 4-row K atoms (rows are contiguous: 512 B)
-                        const uint32_t lbo = p.dbg_swap ? 512u : box_bytes, sbo = p.dbg_swap ? box_bytes : 512u;
+                        const uint32_t lbo = box_bytes, sbo = 512u;
                         const uint64_t ad = bl::umma_smem_desc(a0 + ka * 1024u, lbo, sbo, bl::kLayoutSw128Base32B);
                         const uint64_t bd = bl::umma_smem_desc(b0 + ka * 1024u, lbo, sbo, bl::kLayoutSw128Base32B);
                         bl::umma_tf32(d_tmem, ad, bd, idesc, (ks > 0 || ka > 0) ? 1u : 0u);
@@ -206,10 +205,6 @@ extern "C" int bl_grouped_wgrad(const float* a, const float* b, float* out, int 
     p.out = out;
     p.batch_stride = batch_stride;
     p.vec_ok = (((uintptr_t)out) % 16 == 0) && (batch_stride % 4 == 0) && (N % 4 == 0);
-    {
-        const char* e = getenv("BLADES_WGRAD_SWAP");
-        p.dbg_swap = (e && e[0] == '1') ? 1 : 0;
-    }
     const uint64_t rows = (uint64_t)n_clients * T;
     {
         uint64_t dims[2] = {(uint64_t)M, rows};

@@ -207,6 +207,13 @@ class Simulator(object):
             self._clients[cid] = clients[k]
             self._register_omniscient_callback(clients[k].omniscient_callback)
 
+    def reference_order(self, vec: torch.Tensor) -> torch.Tensor:
+        """Convert an update / aggregate vector (or ``[.., d]`` matrix) from the engine's flat layout to the
+        reference's coordinate order (``named_parameters()`` flattening, client.py:216-228).  On the GPU conv
+        weights are stored channels_last ([Cout, kh, kw, Cin]) inside the flat vector, which permutes the
+        coordinates *within* each conv weight; every built-in aggregator/attack is invariant to that."""
+        return self.engine.gflat.to_reference_order(vec)
+
     # ------------------------------------------------------------------ RNG hygiene
     def cache_random_state(self) -> None:
         if self.device.type == "cuda":
