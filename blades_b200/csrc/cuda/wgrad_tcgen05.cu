@@ -32,6 +32,13 @@ struct WgradParams {
     float* out;              // out[c*batch_stride + m*N + n]
     long long batch_stride;
     int vec_ok;              // 16 B aligned stores possible
+    // ---- implicit-GEMM convolution mode: B rows are gathered from the NHWC activation by TMA (no im2col)
+    CUtensorMap map_x;       // 4D: (Cin, W, H, NB), box (32, bw*cs, bh*cs, bb), element strides (1, cs, cs, 1)
+    int implicit;
+    int Cin, kw, taps;       // N index n = tap * Cin + cin,  tap = r * kw + s
+    int cs, cp;              // conv stride / padding
+    int Ho, Wo, Bc;          // output spatial size, samples per client
+    int bh, bb;              // box: full output rows (Wo) x bh output rows x bb samples  (KT = Wo*bh*bb)
 };
 
 namespace {
@@ -89,9 +96,26 @@ wgrad_tcgen05_kernel(const __grid_constant__ WgradParams p) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         bl::tma_load_2d(dst + j * box_bytes, &p.map_a, &full[s], mt * 128 + j * 32, row);
-                    for (uint32_t j = 0; j < nb_blocks; ++j)
-                        bl::tma_load_2d(dst + a_bytes + j * box_bytes, &p.map_b, &full[s],
-                                        nt * p.BN + (int)j * 32, row);
+                    if (!p.implicit) {
+                        for (uint32_t j = 0; j < nb_blocks; ++j)
+                            bl::tma_load_2d(dst + a_bytes + j * box_bytes, &p.map_b, &full[s],
+                                            nt * p.BN + (int)j * 32, row);
+                    } else {
+                        // K chunk ks = output positions (b0..b0+bb) x (ho0..ho0+bh) x (0..Wo) of client c; for the
+                        // 32-channel block (tap, cin0) the matching input pixels are one strided 4-D TMA box; conv
+                        // padding = out-of-range coordinates, zero-filled by TMA.
+                        const int hchunks = p.Ho / p.bh;
+                        const int b0 = (ks / hchunks) * p.bb, ho0 = (ks % hchunks) * p.bh;
+                        for (uint32_t j = 0; j < nb_blocks; ++j) {
+                            const int n0 = nt * p.BN + (int)j * 32;
+                            const int tap = n0 / p.Cin, cin0 = n0 - tap * p.Cin;
+                            const int r = tap / p.kw, sx = tap - r * p.kw;
+                            const bool valid = tap < p.taps;
+                            bl::tma_load_4d(dst + a_bytes + j * box_bytes, &p.map_x, &full[s],
+                                            valid ? cin0 : p.Cin,           // beyond the channel extent -> zeros
+                                            sx - p.cp, ho0 * p.cs + r - p.cp, c * p.Bc + b0);
+                        }
+                    }
                 }
             }
         }
@@ -227,6 +251,66 @@ extern "C" int bl_grouped_wgrad(const float* a, const float* b, float* out, int 
     p.stages = stages;
     const size_t smem = stages * stage_bytes + 256 + 8 * 32 * kEpiLd * sizeof(float);
     static bool attr_done = false;       // opt in to the full 227 KB once (not a stream op: keep it out of graph capture)
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    const long long total = (long long)n_clients * p.m_tiles * p.n_tiles;
+    int grid = num_sms > 0 ? num_sms : 148;
+    if ((long long)grid > total) grid = (int)total;
+    wgrad_tcgen05_kernel<<<grid, kWThreads, smem, (cudaStream_t)stream>>>(p);
+    return (int)cudaGetLastError();
+}
+
+
+// Implicit-GEMM per-client conv weight gradient: gy [NB*Ho*Wo, Cout] (NHWC rows), x [NB, H, W, Cin] (NHWC),
+// out[c][Cout][kh*kw*Cin] -- the im2col matrix is never materialised.
+extern "C" int bl_conv_wgrad_implicit(const float* gy, const float* x, float* out, int n_clients, int Bc, int H,
+                                      int W, int Cin, int Ho, int Wo, int Cout, int kh, int kw, int cs, int cp,
+                                      long long batch_stride, float alpha, int num_sms, void* stream) {
+    if (Cin % 32 != 0 || Cout % 4 != 0 || cs < 1 || cs > 8 || Wo > 32 || Wo * cs > 256) return -1;
+    if (((uintptr_t)gy) % 16 != 0 || ((uintptr_t)x) % 16 != 0) return -1;
+    // K chunk of ~32 output positions: whole output rows, then whole images
+    int bh = 32 / Wo; if (bh < 1) bh = 1; if (bh > Ho) bh = Ho;
+    while (Ho % bh != 0) --bh;
+    int bb = 1;
+    if (bh == Ho) { bb = 32 / (Wo * Ho); if (bb < 1) bb = 1; if (bb > Bc) bb = Bc; while (Bc % bb != 0) --bb; }
+    const int KT = Wo * bh * bb;
+    if (KT % 8 != 0 || KT > 256 || bh * cs > 256) return -1;
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    const int T = Bc * Ho * Wo, M = Cout, N = kh * kw * Cin;
+    p.n_clients = n_clients; p.T = T; p.M = M; p.N = N; p.KT = KT;
+    int bn = (N + 31) / 32 * 32; if (bn > 256) bn = 256;
+    p.BN = bn; p.m_tiles = (M + 127) / 128; p.n_tiles = (N + bn - 1) / bn;
+    p.alpha = alpha; p.out = out; p.batch_stride = batch_stride;
+    p.vec_ok = (((uintptr_t)out) % 16 == 0) && (batch_stride % 4 == 0) && (N % 4 == 0);
+    p.implicit = 1; p.Cin = Cin; p.kw = kw; p.taps = kh * kw; p.cs = cs; p.cp = cp; p.Ho = Ho; p.Wo = Wo; p.Bc = Bc;
+    p.bh = bh; p.bb = bb;
+    const uint64_t rows = (uint64_t)n_clients * T;
+    {
+        uint64_t dims[2] = {(uint64_t)M, rows};
+        uint64_t strides[1] = {(uint64_t)M * 4};
+        uint32_t box[2] = {32, (uint32_t)KT};
+        int r = bl::make_tmap_f32(&p.map_a, gy, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (r != 0) return 1000 + r;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)n_clients * Bc};
+        uint64_t strides[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
+        uint32_t box[4] = {32, (uint32_t)(Wo * cs), (uint32_t)(bh * cs), (uint32_t)bb};
+        uint32_t es[4] = {1, (uint32_t)cs, (uint32_t)cs, 1};
+        int r = bl::make_tmap_f32(&p.map_x, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, es);
+        if (r != 0) return 2000 + r;
+    }
+    const size_t stage_bytes = (size_t)(4 + bn / 32) * p.KT * 128;
+    int stages = (int)((180 * 1024) / stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages < 2) return -2;
+    p.stages = stages;
+    const size_t smem = stages * stage_bytes + 256 + 8 * 32 * kEpiLd * sizeof(float);
+    static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;

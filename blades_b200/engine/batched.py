@@ -137,6 +137,16 @@ class _ConvFn(torch.autograd.Function):
             # K ordered (r, s, cin) = physical order of the channels_last weight
             if gy.is_cuda:
                 gy = gy.contiguous(memory_format=torch.channels_last)
+                from ..ops import wgrad as _w
+                out3 = sink.view(ctx.wname).view(n, Cout, -1)
+                if _w.conv_wgrad_implicit(gy, x, out3, n, (kh, kw), stride, padding, dilation, sink.alpha):
+                    sink.written.add(ctx.wname)           # implicit GEMM: no im2col matrix at all
+                    if ctx.bname is not None:
+                        sink.put(ctx.bname, gy.reshape(n, B, Cout, L).sum((1, 3)))
+                    gx = None
+                    if ctx.needs_input_grad[0]:
+                        gx = torch.nn.grad.conv2d_input(x.shape, weight, gy, stride, padding, dilation, 1)
+                    return gx, None, None, None, None, None, None, None, None
             cols = im2col_nhwc(x, (kh, kw), stride, padding, dilation, (Ho, Wo))      # [NB*L, K] (padded rows)
             b = cols.as_strided((n, B * L, cols.shape[1]), (B * L * cols.stride(0), cols.stride(0), 1))
             a_t = gy.permute(0, 2, 3, 1).reshape(n, B * L, Cout)                      # view: no copy

@@ -29,3 +29,46 @@ def grouped_wgrad(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, alpha: fl
                 return out
     torch.baddbmm(out, a, b, beta=0.0, alpha=alpha, out=out)
     return out
+
+
+#: BLADES_IMPLICIT_WGRAD=0 forces the explicit im2col + grouped GEMM path for convolutions
+_USE_IMPLICIT = os.environ.get("BLADES_IMPLICIT_WGRAD", "1") != "0"
+
+
+def conv_wgrad_implicit(gy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, n_clients: int, kernel, stride,
+                        padding, dilation, alpha: float) -> bool:
+    """Per-client conv weight gradient WITHOUT materialising im2col: the tcgen05 kernel gathers its B operand
+    straight from the NHWC activation with strided 4-D TMA boxes (padding = TMA out-of-bounds zero fill).
+
+    gy: channels_last ``[NB, Cout, Ho, Wo]``; x: channels_last ``[NB, Cin, H, W]``;
+    out: ``[n, Cout, kh*kw*Cin]`` window of the update matrix (physical channels_last weight order).
+    Returns False when the shape is not supported (caller falls back to im2col + grouped GEMM)."""
+    if not (_USE_KERNEL and _USE_IMPLICIT and gy.is_cuda):
+        return False
+    import ctypes as C
+    from . import _loader
+    lib = _loader.cuda_lib()
+    NB, Cin, H, W = x.shape
+    _, Cout, Ho, Wo = gy.shape
+    kh, kw = kernel
+    if tuple(dilation) != (1, 1) or stride[0] != stride[1] or padding[0] != padding[1]:
+        return False
+    if Cin % 32 or Cout % 4 or Wo > 32 or out.stride(2) != 1 or out.stride(1) != kh * kw * Cin:
+        return False
+    xp, gp = x.permute(0, 2, 3, 1), gy.permute(0, 2, 3, 1)
+    if not (xp.is_contiguous() and gp.is_contiguous()) or x.dtype != torch.float32 or gy.dtype != torch.float32:
+        return False
+    from ._wgrad_impl import _SMS
+    idx = out.device.index or 0
+    if idx not in _SMS:
+        _SMS[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    lib.bl_conv_wgrad_implicit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 12 + \
+        [C.c_longlong, C.c_float, C.c_int, C.c_void_p]
+    code = lib.bl_conv_wgrad_implicit(gp.data_ptr(), xp.data_ptr(), out.data_ptr(), n_clients, NB // n_clients, H, W,
+                                      Cin, Ho, Wo, Cout, kh, kw, stride[0], padding[0], out.stride(0), float(alpha),
+                                      _SMS[idx], _loader.stream_ptr(out.device))
+    if code in (-1, -2):
+        return False
+    _loader.check(code, "conv_wgrad_implicit")
+    _loader.count_launch()
+    return True

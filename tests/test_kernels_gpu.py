@@ -432,3 +432,30 @@ def test_gpu_checkpoint_resume_with_prefetch(tmp_path):
     make().run(mb, global_rounds=7, local_steps=1, server_lr=1.0, client_lr=0.1, validate_interval=7, resume=ck)
     resumed = torch.cat([p.detach().cpu().reshape(-1) for p in mb.parameters()])
     assert torch.allclose(resumed, full, atol=1e-6), (resumed - full).abs().max()
+
+
+@pytest.mark.parametrize("shape", [(3, 32, 64, 8, 8, 64, 3, 1, 1), (2, 32, 64, 8, 8, 128, 3, 2, 1), (2, 32, 128, 4, 4, 128, 3, 1, 1),
+                                   (3, 32, 256, 2, 2, 512, 3, 2, 1), (4, 32, 512, 1, 1, 512, 3, 1, 1), (2, 32, 64, 8, 8, 128, 1, 2, 0),
+                                   (2, 16, 64, 16, 16, 64, 3, 1, 1), (1, 8, 32, 6, 6, 40, 3, 1, 1)])
+def test_conv_wgrad_implicit(shape):
+    """Implicit-GEMM wgrad (4-D strided TMA gather, no im2col) vs autograd's per-client conv weight gradient."""
+    import torch.nn.functional as F
+    from blades_b200.ops import wgrad, _loader
+    n, B, Cin, H, W, Cout, k, s, p = shape
+    x = torch.randn(n * B, Cin, H, W, device=_dev()).contiguous(memory_format=torch.channels_last)
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    gy = torch.randn(n * B, Cout, Ho, Wo, device=_dev()).contiguous(memory_format=torch.channels_last)
+    K = k * k * Cin
+    U = torch.zeros(n, Cout * K + 128, device=_dev())
+    out = U[:, 64: 64 + Cout * K].view(n, Cout, K)
+    before = _loader.LAUNCHES
+    ok = wgrad.conv_wgrad_implicit(gy, x, out, n, (k, k), (s, s), (p, p), (1, 1), -0.1)
+    assert ok and _loader.LAUNCHES == before + 1
+    for c in range(n):
+        w = torch.zeros(Cout, Cin, k, k, device=_dev(), requires_grad=True)
+        y = F.conv2d(x[c * B:(c + 1) * B].double(), w.double(), None, s, p)
+        (g,) = torch.autograd.grad(y, w, gy[c * B:(c + 1) * B].double())
+        ref = -0.1 * g.permute(0, 2, 3, 1).reshape(Cout, K)           # physical channels_last order
+        err = (out[c].double() - ref).abs().max().item()
+        assert err <= 3e-3 * ref.abs().max().item() + 1e-4, (c, err)
+    assert U[:, :64].abs().sum() == 0 and U[:, 64 + Cout * K:].abs().sum() == 0
