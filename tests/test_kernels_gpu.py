@@ -450,6 +450,9 @@ def test_conv_wgrad_implicit(shape):
     out = U[:, 64: 64 + Cout * K].view(n, Cout, K)
     before = _loader.LAUNCHES
     ok = wgrad.conv_wgrad_implicit(gy, x, out, n, (k, k), (s, s), (p, p), (1, 1), -0.1)
+    if Wo * max(1, min(Ho, 32 // Wo)) % 8:          # K chunk (whole output rows) not a multiple of 8: unsupported
+        assert not ok
+        return
     assert ok and _loader.LAUNCHES == before + 1
     for c in range(n):
         w = torch.zeros(Cout, Cin, k, k, device=_dev(), requires_grad=True)
