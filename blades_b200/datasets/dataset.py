@@ -113,6 +113,29 @@ class FLDataset:
                                       sample_bytes, bx.data_ptr(), by.data_ptr())
         return bx, by
 
+    # ------------------------------------------------------------------ zero-copy device gather
+    def device_gather_plan(self, client_ids: Sequence[int]):
+        """If every listed client streams untransformed float32 samples, pin the per-client arrays once and
+        return ``(streams, sample_shape, batch_size)`` so a GPU kernel can gather mini-batches straight from
+        pinned host memory (``ops.gather``); otherwise ``None``."""
+        from .basedataset import BatchStream
+        streams = [self._train_dls[c] for c in client_ids]
+        if not streams or not all(isinstance(s, BatchStream) and s.transform is None and s.data.dtype == np.float32
+                                  and s.labels.dtype == np.int64 and len(s.labels) >= s.batch_size
+                                  and len(s.labels) % s.batch_size == 0 for s in streams):
+            return None                                  # (ragged tail batches go through the host path)
+        bs, shp = streams[0].batch_size, streams[0].data.shape[1:]
+        if not all(s.batch_size == bs and s.data.shape[1:] == shp for s in streams):
+            return None
+        for s in streams:
+            if not getattr(s, "_pinned", False):
+                px = torch.from_numpy(np.ascontiguousarray(s.data)).pin_memory()
+                py = torch.from_numpy(np.ascontiguousarray(s.labels)).pin_memory()
+                s._pin_keep = (px, py)                 # keep the pinned storage alive
+                s.data, s.labels = px.numpy(), py.numpy()
+                s._pinned = True
+        return streams, tuple(shp), bs
+
     def _ragged_restart(self):
         raise ValueError("ragged batch (client shard not a multiple of the batch size); use get_train_data")
 

@@ -119,6 +119,8 @@ class RoundEngine:
         self.kernel_launches = 0
         self._clamps = {}
         self._pf_pool = None
+        self._pf_stream = None
+        self._zc_plans = {}
         self._pf_jobs = {}
         self._pf_last = None
         self._cursor_after = {}
@@ -235,11 +237,15 @@ class RoundEngine:
 
     def _pf_submit(self, rows, num_batches):
         import concurrent.futures as cf
+        zc = self._zero_copy_submit(rows, num_batches)
+        if zc is not None:
+            return zc
         if self._pf_pool is None:
             self._pf_pool = cf.ThreadPoolExecutor(max_workers=1, thread_name_prefix="blades-prefetch")
-            self._pf_stream = torch.cuda.Stream(device=self.device)
+            if self._pf_stream is None:
+                self._pf_stream = torch.cuda.Stream(device=self.device)
+                self._pf_slot = 0
             self._pf_dev = {}
-            self._pf_slot = 0
         slot = self._pf_slot
         self._pf_slot ^= 1
         # the device staging buffer of this slot was last read by work enqueued on the main stream
@@ -264,6 +270,69 @@ class RoundEngine:
                 ev.record(self._pf_stream)
             return bufs[0], bufs[1], ev, slot
         return self._pf_pool.submit(job)
+
+    def _zero_copy_submit(self, rows, num_batches):
+        """Next round's inputs via the zero-copy gather kernel: host work = drawing the index list."""
+        import os
+        if os.environ.get("BLADES_ZERO_COPY", "1") == "0":
+            return None
+        key = (tuple(rows), num_batches)
+        plan = self._zc_plans.get(key)
+        if plan is None:
+            ids = [self.clients[self.local_idx[r]].id() for r in rows]
+            got = self.dataset.device_gather_plan(ids) if hasattr(self.dataset, "device_gather_plan") else None
+            if got is None:
+                self._zc_plans[key] = False
+                return None
+            streams, shp, bs = got
+            n, per = len(streams), num_batches * bs
+            tab_x = torch.tensor([s.data.ctypes.data for s in streams], dtype=torch.int64).to(self.device)
+            tab_y = torch.tensor([s.labels.ctypes.data for s in streams], dtype=torch.int64).to(self.device)
+            sample_floats = int(np.prod(shp))
+            plan = self._zc_plans[key] = dict(
+                streams=streams, n=n, per=per, bs=bs, tab_x=tab_x, tab_y=tab_y, sample_floats=sample_floats,
+                h_idx=[torch.empty(n * per, dtype=torch.int64).pin_memory() for _ in range(2)],
+                d_idx=[torch.empty(n * per, dtype=torch.int64, device=self.device) for _ in range(2)],
+                X=[torch.empty((n, num_batches, bs) + shp, dtype=torch.float32, device=self.device) for _ in range(2)],
+                y=[torch.empty((n, num_batches, bs), dtype=torch.int64, device=self.device) for _ in range(2)],
+                idx_done=[None, None])
+            if self._pf_stream is None:
+                self._pf_stream = torch.cuda.Stream(device=self.device)
+                self._pf_slot = 0
+        elif plan is False:
+            return None
+        from ..ops import gather as kg
+        slot = self._pf_slot
+        self._pf_slot ^= 1
+        if plan["idx_done"][slot] is not None:
+            plan["idx_done"][slot].synchronize()         # the pinned index buffer of this slot is free again
+        h = plan["h_idx"][slot].numpy().reshape(plan["n"], plan["per"])
+        bs = plan["bs"]
+        for i, st in enumerate(plan["streams"]):
+            for j in range(plan["per"] // bs):
+                h[i, j * bs:(j + 1) * bs] = st.next_indices()
+        if self.track_cursors:
+            self._cursor_after[slot] = self.dataset.state_dict()
+        consumed = torch.cuda.Event()
+        consumed.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self._pf_stream):
+            self._pf_stream.wait_event(consumed)
+            plan["d_idx"][slot].copy_(plan["h_idx"][slot], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._pf_stream)
+            plan["idx_done"][slot] = done
+            kg.gather_samples(plan["tab_x"], plan["tab_y"], plan["d_idx"][slot], plan["X"][slot], plan["y"][slot],
+                              plan["per"], plan["sample_floats"])
+            ev = torch.cuda.Event()
+            ev.record(self._pf_stream)
+
+        class _Done:
+            def __init__(self, v):
+                self.v = v
+
+            def result(self):
+                return self.v
+        return _Done((plan["X"][slot], plan["y"][slot], ev, slot))
 
     def data_cursors(self):
         """Data-stream cursors as of the batches consumed so far (the prefetcher runs one round ahead)."""

@@ -450,7 +450,16 @@ def test_conv_wgrad_implicit(shape):
     out = U[:, 64: 64 + Cout * K].view(n, Cout, K)
     before = _loader.LAUNCHES
     ok = wgrad.conv_wgrad_implicit(gy, x, out, n, (k, k), (s, s), (p, p), (1, 1), -0.1)
-    if Wo * max(1, min(Ho, 32 // Wo)) % 8:          # K chunk (whole output rows) not a multiple of 8: unsupported
+    # mirror the launcher's K-chunk choice (whole output rows, then whole samples): it must be a multiple of 8
+    bh = max(1, min(Ho, 32 // Wo))
+    while Ho % bh:
+        bh -= 1
+    bb = 1
+    if bh == Ho:
+        bb = max(1, min(B, 32 // (Wo * Ho)))
+        while B % bb:
+            bb -= 1
+    if (Wo * bh * bb) % 8 or Cin % 32 or Cout % 4:
         assert not ok
         return
     assert ok and _loader.LAUNCHES == before + 1
