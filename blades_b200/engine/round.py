@@ -122,6 +122,7 @@ class RoundEngine:
         self._pf_stream = None
         self._zc_plans = {}
         self._pf_jobs = {}
+        self._pf_deferred = None
         self._pf_last = None
         self._cursor_after = {}
         self.track_cursors = False
@@ -220,24 +221,36 @@ class RoundEngine:
             nb = self.device.type == "cuda"
             return X.to(self.device, non_blocking=nb), y.to(self.device, non_blocking=nb)
         key = (tuple(rows), num_batches)
+        self.flush_prefetch()
         fut = self._pf_jobs.pop(key, None)
         if fut is None:
             fut = self._pf_submit(rows, num_batches)
         X, y, ev, slot = fut.result()
         torch.cuda.current_stream(self.device).wait_event(ev)
         self.h2d_bytes = X.numel() * X.element_size() + y.numel() * y.element_size()
-        # consumers enqueue their reads right after this call; the slot may be refilled two rounds later
+        # consumers enqueue their reads right after this call; the slot may be refilled two rounds later.
+        # The request for round r+1 is issued by flush_prefetch() AFTER this round's work has been launched
+        # (its host part then overlaps the GPU), but ordered against the reads enqueued so far.
         self._pf_last = (key, slot)
-        self._pf_jobs[key] = self._pf_submit(rows, num_batches)
+        consumed = torch.cuda.Event()
+        consumed.record(torch.cuda.current_stream(self.device))
+        self._pf_deferred = (key, rows, num_batches, consumed)
         return X, y
+
+    def flush_prefetch(self) -> None:
+        """Issue the deferred request for the next round's inputs (called right after a round is launched)."""
+        d, self._pf_deferred = self._pf_deferred, None
+        if d is not None:
+            key, rows, num_batches, consumed = d
+            self._pf_jobs[key] = self._pf_submit(rows, num_batches, consumed)
 
     def _assemble(self, rows, num_batches, slot):
         ids = [self.clients[self.local_idx[r]].id() for r in rows]
         return self.dataset.get_train_batches(ids, num_batches, slot=slot)
 
-    def _pf_submit(self, rows, num_batches):
+    def _pf_submit(self, rows, num_batches, consumed=None):
         import concurrent.futures as cf
-        zc = self._zero_copy_submit(rows, num_batches)
+        zc = self._zero_copy_submit(rows, num_batches, consumed)
         if zc is not None:
             return zc
         if self._pf_pool is None:
@@ -249,8 +262,9 @@ class RoundEngine:
         slot = self._pf_slot
         self._pf_slot ^= 1
         # the device staging buffer of this slot was last read by work enqueued on the main stream
-        consumed = torch.cuda.Event()
-        consumed.record(torch.cuda.current_stream(self.device))
+        if consumed is None:
+            consumed = torch.cuda.Event()
+            consumed.record(torch.cuda.current_stream(self.device))
 
         def job():
             torch.cuda.set_device(self.device)
@@ -271,7 +285,7 @@ class RoundEngine:
             return bufs[0], bufs[1], ev, slot
         return self._pf_pool.submit(job)
 
-    def _zero_copy_submit(self, rows, num_batches):
+    def _zero_copy_submit(self, rows, num_batches, consumed=None):
         """Next round's inputs via the zero-copy gather kernel: host work = drawing the index list."""
         import os
         if os.environ.get("BLADES_ZERO_COPY", "1") == "0":
@@ -313,8 +327,9 @@ class RoundEngine:
                 h[i, j * bs:(j + 1) * bs] = st.next_indices()
         if self.track_cursors:
             self._cursor_after[slot] = self.dataset.state_dict()
-        consumed = torch.cuda.Event()
-        consumed.record(torch.cuda.current_stream(self.device))
+        if consumed is None:
+            consumed = torch.cuda.Event()
+            consumed.record(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self._pf_stream):
             self._pf_stream.wait_event(consumed)
             plan["d_idx"][slot].copy_(plan["h_idx"][slot], non_blocking=True)
@@ -389,6 +404,7 @@ class RoundEngine:
         sx.copy_(X, non_blocking=True)
         sy.copy_(y, non_blocking=True)
         graph.replay()
+        self.flush_prefetch()
         from ..ops import _loader
         _loader.count_launch(n_native)               # our kernels inside the replayed graph
         self.last_client_losses = losses
@@ -449,6 +465,7 @@ class RoundEngine:
         st["sx"].copy_(X, non_blocking=True)
         st["sy"].copy_(y, non_blocking=True)
         st["graph"].replay()
+        self.flush_prefetch()
         _loader.count_launch(st["n_native"])
         self.last_client_losses = st["losses"]
         self.static_aggregate = st["agg"]
