@@ -165,14 +165,17 @@ def run_ours(args) -> dict:
         torch.cuda.synchronize()
         world.barrier()
         t0 = time.perf_counter()
+        per_round = []
         for r in range(args.steps):
-            one_round(r)                                   # host batches -> pinned -> H2D -> round
+            tr = time.perf_counter()
+            one_round(r)                                   # host indices -> gather from pinned host memory -> round
             if eng.last_client_losses is not None:
                 loss_host = eng.last_client_losses.cpu()   # D2H read of the step's result
                 d2h = loss_host.numel() * loss_host.element_size()
             else:
                 loss_host = sim.last_aggregate[:1].cpu()
                 d2h = 4
+            per_round.append((time.perf_counter() - tr) * 1e3)
         torch.cuda.synchronize()
         world.barrier()
         e2e_ms = world.all_reduce_max((time.perf_counter() - t0) * 1e3)
@@ -195,7 +198,8 @@ def run_ours(args) -> dict:
     }
     if e2e_ms is not None:
         out["e2e"] = {"value": args.steps / (e2e_ms / 1e3), "unit": "rounds/s", "ms_per_step": e2e_ms / args.steps,
-                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                      "round_ms_median_rank0": sorted(per_round)[len(per_round) // 2], "round_ms_max_rank0": max(per_round)}
     return out if world.rank == 0 else {}
 
 
