@@ -223,6 +223,8 @@ def run_reference(args) -> dict:
            str(args.warmup), "--gpus", str(args.gpus), "--clients", str(n_clients), "--byzantine", str(n_byz),
            "--batch", str(args.batch), "--model", model_name, "--budget", str(budget)]
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    if "WORLD_SIZE" in os.environ:
+        env.pop("OMP_NUM_THREADS", None)       # torchrun pins it to 1; the reference aggregates on the CPU
     proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True,
                             env=env)
     try:

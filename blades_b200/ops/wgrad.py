@@ -35,14 +35,21 @@ def grouped_wgrad(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, alpha: fl
 _USE_IMPLICIT = os.environ.get("BLADES_IMPLICIT_WGRAD", "1") != "0"
 
 
+_IMPLICIT_MAX_T = int(os.environ.get("BLADES_IMPLICIT_MAX_T", "1024"))
+
+
 def conv_wgrad_implicit(gy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, n_clients: int, kernel, stride,
-                        padding, dilation, alpha: float) -> bool:
+                        padding, dilation, alpha: float, force: bool = False) -> bool:
     """Per-client conv weight gradient WITHOUT materialising im2col: the tcgen05 kernel gathers its B operand
     straight from the NHWC activation with strided 4-D TMA boxes (padding = TMA out-of-bounds zero fill).
 
     gy: channels_last ``[NB, Cout, Ho, Wo]``; x: channels_last ``[NB, Cin, H, W]``;
     out: ``[n, Cout, kh*kw*Cin]`` window of the update matrix (physical channels_last weight order).
-    Returns False when the shape is not supported (caller falls back to im2col + grouped GEMM)."""
+    Returns False when the shape is not supported (caller falls back to im2col + grouped GEMM), or -- unless
+    ``force`` -- when the per-client reduction length T = B*Ho*Wo exceeds ``BLADES_IMPLICIT_MAX_T`` (default 1024):
+    measured on B200 (profiles/round_kernels_r1.txt) the 4-D gather runs the long-K / small-output layers
+    (ResNet layer1: T = 2048, 64 x 576 outputs) at 329 us vs 162 us + ~100 us im2col for the explicit pair, while
+    it wins or ties from T = 512 down (and saves the im2col matrix)."""
     if not (_USE_KERNEL and _USE_IMPLICIT and gy.is_cuda):
         return False
     import ctypes as C
@@ -54,6 +61,8 @@ def conv_wgrad_implicit(gy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, n_
     if tuple(dilation) != (1, 1) or stride[0] != stride[1] or padding[0] != padding[1]:
         return False
     if Cin % 32 or Cout % 4 or Wo > 32 or out.stride(2) != 1 or out.stride(1) != kh * kw * Cin:
+        return False
+    if not force and (NB // n_clients) * Ho * Wo > _IMPLICIT_MAX_T:
         return False
     xp, gp = x.permute(0, 2, 3, 1), gy.permute(0, 2, 3, 1)
     if not (xp.is_contiguous() and gp.is_contiguous()) or x.dtype != torch.float32 or gy.dtype != torch.float32:

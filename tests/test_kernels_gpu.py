@@ -449,7 +449,7 @@ def test_conv_wgrad_implicit(shape):
     U = torch.zeros(n, Cout * K + 128, device=_dev())
     out = U[:, 64: 64 + Cout * K].view(n, Cout, K)
     before = _loader.LAUNCHES
-    ok = wgrad.conv_wgrad_implicit(gy, x, out, n, (k, k), (s, s), (p, p), (1, 1), -0.1)
+    ok = wgrad.conv_wgrad_implicit(gy, x, out, n, (k, k), (s, s), (p, p), (1, 1), -0.1, force=True)
     # mirror the launcher's K-chunk choice (whole output rows, then whole samples): it must be a multiple of 8
     bh = max(1, min(Ho, 32 // Wo))
     while Ho % bh:
