@@ -108,6 +108,17 @@ class _LinearFn(torch.autograd.Function):
         return gx, None, None, None, None, None
 
 
+def _conv_dgrad(gy, x, weight, stride, padding, dilation):
+    """Input gradient of conv2d.  ``torch.nn.grad.conv2d_input`` hands cuDNN a stride-0 dummy of the input's
+    shape, which the backend then materialises with ``.contiguous()`` -- a full activation-sized copy per layer
+    (measured: 20 copies, 0.31 ms of an 11 ms ResNet-18 round).  Passing the real saved input costs nothing and
+    keeps the result channels_last."""
+    def pair(v):
+        return [v, v] if isinstance(v, int) else list(v)
+    return torch.ops.aten.convolution_backward(gy, x, weight, None, pair(stride), pair(padding), pair(dilation),
+                                               False, [0, 0], 1, [True, False, False])[0]
+
+
 class _ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, sink, wname, bname, stride, padding, dilation):
@@ -145,7 +156,7 @@ class _ConvFn(torch.autograd.Function):
                         sink.put(ctx.bname, gy.reshape(n, B, Cout, L).sum((1, 3)))
                     gx = None
                     if ctx.needs_input_grad[0]:
-                        gx = torch.nn.grad.conv2d_input(x.shape, weight, gy, stride, padding, dilation, 1)
+                        gx = _conv_dgrad(gy, x, weight, stride, padding, dilation)
                     return gx, None, None, None, None, None, None, None, None
             cols = im2col_nhwc(x, (kh, kw), stride, padding, dilation, (Ho, Wo))      # [NB*L, K] (padded rows)
             b = cols.as_strided((n, B * L, cols.shape[1]), (B * L * cols.stride(0), cols.stride(0), 1))
@@ -158,7 +169,7 @@ class _ConvFn(torch.autograd.Function):
             sink.put(ctx.bname, gy.reshape(n, B, Cout, L).sum((1, 3)))
         gx = None
         if ctx.needs_input_grad[0]:
-            gx = torch.nn.grad.conv2d_input(x.shape, weight, gy, stride, padding, dilation, 1)
+            gx = _conv_dgrad(gy, x, weight, stride, padding, dilation)
         return gx, None, None, None, None, None, None, None, None
 
 
