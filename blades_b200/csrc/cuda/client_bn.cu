@@ -260,14 +260,262 @@ client_bn_nhwc_bwd_kernel(const __grid_constant__ ClientBNParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cluster variants (default).  The plain NHWC kernels above launch only ceil(C/32) * n CTAs (200 for the stem BN of
+// ResNet-18 at 100 clients: 1.35 CTAs per SM) and stream x from DRAM up to three times, because the ~2 MB
+// per-client slices of all resident CTAs together do not fit L2.  Here a thread-block CLUSTER of S CTAs owns one
+// (client, channel tile): CTA r stages rows [r*R/S, (r+1)*R/S) of the tile in shared memory while it accumulates
+// its partial sums, the S partials are exchanged through distributed shared memory (one float4 per channel quad),
+// and every later pass (exact two-pass variance, normalisation; dx in the backward) runs out of shared memory.
+// x (and gy) cross HBM exactly once, y/dx once; the grid is S times larger.
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+template <int QUADS>
+__device__ __forceinline__ float4 bn_cl_reduce4(float4 v, float4* red) {      // red: [256/QUADS][QUADS]
+    constexpr int GROUPS = 256 / QUADS;
+    const int q = threadIdx.x % QUADS, rg = threadIdx.x / QUADS;
+    __syncthreads();
+    red[rg * QUADS + q] = v;
+    __syncthreads();
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int i = 0; i < GROUPS; ++i) {
+        const float4 t = red[i * QUADS + q];
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    return s;
+}
+
+template <int QUADS>
+__device__ __forceinline__ float4 bn_cl_exchange(cg::cluster_group& cluster, float4* part, float4 mine, int slot) {
+    // publish this CTA's partial, then sum the partials of every CTA of the cluster through DSMEM
+    const int q = threadIdx.x % QUADS, rg = threadIdx.x / QUADS;
+    if (rg == 0) part[slot * QUADS + q] = mine;
+    cluster.sync();
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const unsigned S = cluster.num_blocks();
+    for (unsigned j = 0; j < S; ++j) {
+        const float4 t = cluster.map_shared_rank(part, j)[slot * QUADS + q];
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    return s;
+}
+
+template <int QUADS>
+__global__ void __launch_bounds__(256)
+client_bn_nhwc_fwd_cl_kernel(const __grid_constant__ ClientBNParams p) {
+    constexpr int GROUPS = 256 / QUADS;
+    extern __shared__ __align__(16) float4 bn_tile[];          // [Rc][QUADS]
+    __shared__ float4 red[256];
+    __shared__ float4 part[2 * QUADS];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int S = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int c = blockIdx.y;
+    const int q = threadIdx.x % QUADS, rg = threadIdx.x / QUADS;
+    const int ch = (blockIdx.x / S) * (QUADS * 4) + q * 4;
+    const bool live = ch < p.C;
+    const int R = p.B * p.HW, Rc = R / S;
+    const long long base = ((long long)c * R + (long long)rank * Rc) * p.C + ch;
+    const float4* xb = reinterpret_cast<const float4*>(p.x + base);
+    const long long rs = p.C / 4;
+    const float m = (float)R;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+#pragma unroll 8
+        for (int r = rg; r < Rc; r += GROUPS) {
+            const float4 v = __ldcs(&xb[(long long)r * rs]);
+            bn_tile[r * QUADS + q] = v;
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+    }
+    float4 mean = bn_cl_exchange<QUADS>(cluster, part, bn_cl_reduce4<QUADS>(s, red), 0);
+    mean.x /= m; mean.y /= m; mean.z /= m; mean.w /= m;
+    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+#pragma unroll 8
+        for (int r = rg; r < Rc; r += GROUPS) {
+            const float4 v = bn_tile[r * QUADS + q];
+            float d;
+            d = v.x - mean.x; qv.x = fmaf(d, d, qv.x);
+            d = v.y - mean.y; qv.y = fmaf(d, d, qv.y);
+            d = v.z - mean.z; qv.z = fmaf(d, d, qv.z);
+            d = v.w - mean.w; qv.w = fmaf(d, d, qv.w);
+        }
+    }
+    const float4 var = bn_cl_exchange<QUADS>(cluster, part, bn_cl_reduce4<QUADS>(qv, red), 1);
+    if (live) {
+        const float4 rstd = make_float4(rsqrtf(var.x / m + p.eps), rsqrtf(var.y / m + p.eps),
+                                        rsqrtf(var.z / m + p.eps), rsqrtf(var.w / m + p.eps));
+        const float4 ga = *reinterpret_cast<const float4*>(p.gamma + ch);
+        const float4 be = *reinterpret_cast<const float4*>(p.beta + ch);
+        const float4 g = make_float4(ga.x * rstd.x, ga.y * rstd.y, ga.z * rstd.z, ga.w * rstd.w);
+        const float4 sh = make_float4(be.x - mean.x * g.x, be.y - mean.y * g.y, be.z - mean.z * g.z, be.w - mean.w * g.w);
+        float4* yb = reinterpret_cast<float4*>(p.y + base);
+#pragma unroll 8
+        for (int r = rg; r < Rc; r += GROUPS) {
+            const float4 v = bn_tile[r * QUADS + q];
+            yb[(long long)r * rs] = make_float4(fmaf(v.x, g.x, sh.x), fmaf(v.y, g.y, sh.y), fmaf(v.z, g.z, sh.z),
+                                                fmaf(v.w, g.w, sh.w));
+        }
+        if (rg == 0 && rank == 0) {
+            *reinterpret_cast<float4*>(p.mean + c * p.C + ch) = mean;
+            *reinterpret_cast<float4*>(p.rstd + c * p.C + ch) = rstd;
+        }
+    }
+    cluster.sync();                 // peers may still be reading this CTA's partials
+}
+
+template <int QUADS>
+__global__ void __launch_bounds__(256)
+client_bn_nhwc_bwd_cl_kernel(const __grid_constant__ ClientBNParams p) {
+    constexpr int GROUPS = 256 / QUADS;
+    extern __shared__ __align__(16) float4 bn_tile[];          // x tile [Rc][QUADS], then gy tile [Rc][QUADS]
+    __shared__ float4 red[256];
+    __shared__ float4 part[2 * QUADS];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int S = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int c = blockIdx.y;
+    const int q = threadIdx.x % QUADS, rg = threadIdx.x / QUADS;
+    const int ch = (blockIdx.x / S) * (QUADS * 4) + q * 4;
+    const bool live = ch < p.C;
+    const int R = p.B * p.HW, Rc = R / S;
+    const long long base = ((long long)c * R + (long long)rank * Rc) * p.C + ch;
+    const float4* xb = reinterpret_cast<const float4*>(p.x + base);
+    const float4* gb = reinterpret_cast<const float4*>(p.gy + base);
+    float4* xt = bn_tile;
+    float4* gt = bn_tile + (size_t)Rc * QUADS;
+    const long long rs = p.C / 4;
+    float4 mean = make_float4(0.f, 0.f, 0.f, 0.f), rstd = mean;
+    if (live) {
+        mean = *reinterpret_cast<const float4*>(p.mean + c * p.C + ch);
+        rstd = *reinterpret_cast<const float4*>(p.rstd + c * p.C + ch);
+    }
+    float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sg = sb;
+    if (live) {
+#pragma unroll 4
+        for (int r = rg; r < Rc; r += GROUPS) {
+            const float4 g = __ldcs(&gb[(long long)r * rs]), v = __ldcs(&xb[(long long)r * rs]);
+            const float4 xh = make_float4((v.x - mean.x) * rstd.x, (v.y - mean.y) * rstd.y, (v.z - mean.z) * rstd.z,
+                                          (v.w - mean.w) * rstd.w);
+            xt[r * QUADS + q] = xh;             // keep xhat, not x
+            gt[r * QUADS + q] = g;
+            sb.x += g.x; sb.y += g.y; sb.z += g.z; sb.w += g.w;
+            sg.x = fmaf(g.x, xh.x, sg.x); sg.y = fmaf(g.y, xh.y, sg.y);
+            sg.z = fmaf(g.z, xh.z, sg.z); sg.w = fmaf(g.w, xh.w, sg.w);
+        }
+    }
+    const float4 pb = bn_cl_reduce4<QUADS>(sb, red);
+    const float4 pg = bn_cl_reduce4<QUADS>(sg, red);
+    if (rg == 0) part[QUADS + q] = pg;
+    const float4 dbeta = bn_cl_exchange<QUADS>(cluster, part, pb, 0);      // its cluster.sync also publishes part[1]
+    float4 dgamma = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < S; ++j) {
+        const float4 t = cluster.map_shared_rank(part, j)[QUADS + q];
+        dgamma.x += t.x; dgamma.y += t.y; dgamma.z += t.z; dgamma.w += t.w;
+    }
+    if (live) {
+        if (rg == 0 && rank == 0) {
+            float* dg = p.dgamma + (long long)c * p.ld + ch;
+            float* db = p.dbeta + (long long)c * p.ld + ch;
+            dg[0] = bl_sanitize(p.alpha * dgamma.x); dg[1] = bl_sanitize(p.alpha * dgamma.y);
+            dg[2] = bl_sanitize(p.alpha * dgamma.z); dg[3] = bl_sanitize(p.alpha * dgamma.w);
+            db[0] = bl_sanitize(p.alpha * dbeta.x); db[1] = bl_sanitize(p.alpha * dbeta.y);
+            db[2] = bl_sanitize(p.alpha * dbeta.z); db[3] = bl_sanitize(p.alpha * dbeta.w);
+        }
+        if (p.y != nullptr) {
+            const float inv_m = 1.f / (float)R;
+            const float4 ga = *reinterpret_cast<const float4*>(p.gamma + ch);
+            const float4 k = make_float4(ga.x * rstd.x, ga.y * rstd.y, ga.z * rstd.z, ga.w * rstd.w);
+            float4* yb = reinterpret_cast<float4*>(p.y + base);
+#pragma unroll 8
+            for (int r = rg; r < Rc; r += GROUPS) {
+                const float4 g = gt[r * QUADS + q], xh = xt[r * QUADS + q];
+                float4 o;
+                o.x = k.x * (g.x - (dbeta.x + xh.x * dgamma.x) * inv_m);
+                o.y = k.y * (g.y - (dbeta.y + xh.y * dgamma.y) * inv_m);
+                o.z = k.z * (g.z - (dbeta.z + xh.z * dgamma.z) * inv_m);
+                o.w = k.w * (g.w - (dbeta.w + xh.w * dgamma.w) * inv_m);
+                yb[(long long)r * rs] = o;
+            }
+        }
+    }
+    cluster.sync();
+}
+
+namespace {
+constexpr size_t kBnClMaxSmem = 200 * 1024;
+
+// Cluster size S (power of two <= 8, dividing R) and tile width for `tiles_per_row` staged tiles per row:
+// smallest S whose tile fits 64 KB, grown while the grid is below ~4 CTAs per SM; 16-channel tiles when even
+// S = 8 needs more than 96 KB with 32 channels.  Returns false when nothing fits (caller uses the plain kernel).
+bool bn_cl_plan(const ClientBNParams* p, int staged, int* S_out, int* quads_out, size_t* smem_out) {
+    static const bool enabled = [] { const char* e = getenv("BLADES_BN_CLUSTER"); return !(e && e[0] == '0'); }();
+    if (!enabled) return false;
+    const long long R = (long long)p->B * p->HW;
+    // measured (profiles/round_launches_r1.txt vs round_kernels2): the cluster form wins for long slices staged in
+    // <= 64 KB per CTA (stem BN fwd 269 -> 175 us, layer1 fwd 40 -> 28 us, bwd 74 -> 64 us) and loses for short
+    // slices (R <= 512: 12 -> 18 us, launch/sync overhead) and for the stem backward, whose two staged tiles need
+    // 128 KB per CTA (one CTA per SM: 277 -> 425 us).
+    if (R < 1024) return false;
+    int quads = 8;
+    auto bytes = [&](int S, int qd) { return (size_t)(R / S) * qd * 16 * staged; };
+    int S = 1;
+    while (S < 8 && R % (2 * S) == 0 && bytes(S, quads) > 64 * 1024) S *= 2;
+    if (bytes(S, quads) > 96 * 1024 && p->C % 16 == 0) quads = 4;
+    if (bytes(S, quads) > 64 * 1024) return false;
+    auto ctas = [&](int S_, int qd) { return (long long)((p->C + qd * 4 - 1) / (qd * 4)) * p->n * S_; };
+    while (S < 8 && R % (2 * S) == 0 && R / (2 * S) >= 256 / quads && ctas(S, quads) < 600) S *= 2;
+    *S_out = S; *quads_out = quads; *smem_out = bytes(S, quads);
+    return true;
+}
+
+template <typename K>
+int bn_cl_launch(K kernel, const ClientBNParams* p, int S, int quads, size_t smem, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(((p->C + quads * 4 - 1) / (quads * 4)) * S), (unsigned)p->n);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, kernel, *p);
+}
+
+void bn_cl_set_attrs() {
+    static const bool once = [] {
+        cudaFuncSetAttribute(client_bn_nhwc_fwd_cl_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBnClMaxSmem);
+        cudaFuncSetAttribute(client_bn_nhwc_fwd_cl_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBnClMaxSmem);
+        cudaFuncSetAttribute(client_bn_nhwc_bwd_cl_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBnClMaxSmem);
+        cudaFuncSetAttribute(client_bn_nhwc_bwd_cl_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBnClMaxSmem);
+        return true;
+    }();
+    (void)once;
+}
+}  // namespace
+
 extern "C" int bl_client_bn_nhwc_fwd(const ClientBNParams* p, void* stream) {
     if (p->C % 4 != 0) return -1;
+    int S, quads; size_t smem;
+    if (bn_cl_plan(p, 1, &S, &quads, &smem)) {
+        bn_cl_set_attrs();
+        return quads == 8 ? bn_cl_launch(client_bn_nhwc_fwd_cl_kernel<8>, p, S, quads, smem, (cudaStream_t)stream)
+                          : bn_cl_launch(client_bn_nhwc_fwd_cl_kernel<4>, p, S, quads, smem, (cudaStream_t)stream);
+    }
     dim3 grid((p->C + kBnTile - 1) / kBnTile, p->n);
     client_bn_nhwc_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
     return (int)cudaGetLastError();
 }
 extern "C" int bl_client_bn_nhwc_bwd(const ClientBNParams* p, void* stream) {
     if (p->C % 4 != 0) return -1;
+    int S, quads; size_t smem;
+    if (bn_cl_plan(p, 2, &S, &quads, &smem)) {
+        bn_cl_set_attrs();
+        return quads == 8 ? bn_cl_launch(client_bn_nhwc_bwd_cl_kernel<8>, p, S, quads, smem, (cudaStream_t)stream)
+                          : bn_cl_launch(client_bn_nhwc_bwd_cl_kernel<4>, p, S, quads, smem, (cudaStream_t)stream);
+    }
     dim3 grid((p->C + kBnTile - 1) / kBnTile, p->n);
     client_bn_nhwc_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
     return (int)cudaGetLastError();

@@ -323,7 +323,7 @@ def test_im2col_nhwc(shape):
     assert got.stride(0) % 4 == 0
 
 
-@pytest.mark.parametrize("n,B,C,H", [(5, 32, 64, 16), (3, 32, 64, 8), (4, 16, 128, 4), (7, 32, 512, 1), (2, 8, 24, 7)])
+@pytest.mark.parametrize("n,B,C,H", [(5, 32, 64, 16), (3, 32, 64, 8), (4, 16, 128, 4), (7, 32, 512, 1), (2, 8, 24, 7), (3, 5, 16, 3), (1, 32, 64, 16)])
 def test_client_bn_nhwc_kernels(n, B, C, H):
     from blades_b200.ops import client_bn as kbn
     x = (torch.randn(n * B, C, H, H, device=_dev()) * 2 + 0.5).contiguous(memory_format=torch.channels_last)
