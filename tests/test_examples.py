@@ -37,3 +37,26 @@ def test_main_script_cli(tmp_path):
                           "--data_root", str(tmp_path / "data")], capture_output=True, text=True, env=env, cwd=tmp_path)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "2 rounds" in out.stdout
+
+
+def test_aggregator_sweep_example(tmp_path, monkeypatch):
+    """examples/simulation_on_mnist.py: five defences under IPM, stats logs read back into one table."""
+    monkeypatch.chdir(tmp_path)
+    from blades_b200.examples.simulation_on_mnist import AGGS, main
+    df = main(rounds=2, local_steps=2, out_root=str(tmp_path / "outputs"))
+    assert set(df["AGG"]) == set(AGGS) and len(df) == 2 * len(AGGS)
+    assert {"Round Number", "Accuracy (%)", "Loss"} <= set(df.columns)
+
+
+def test_fltrust_example(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    from blades_b200.examples.fltrust_example import main
+    sim = main(rounds=2)
+    assert sum(c.is_trusted() for c in sim.get_clients()) == 1
+
+
+def test_cifar10_example_small(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    from blades_b200.examples.cifar10_example import main
+    _, times = main(dataset="cifar10", rounds=1, local_steps=1, num_clients=4, num_byzantine=1)
+    assert len(times) == 1
