@@ -22,7 +22,7 @@ class Fltrust(_BaseAggregator):
     def __call__(self, inputs):
         from ..client import BladesClient
         seq = list(inputs) if not hasattr(inputs, "n_rows") and not hasattr(inputs, "dim") else None
-        if seq is not None and len(seq) and all(isinstance(c, BladesClient) for c in seq):
+        if seq is not None and len(seq) and all(isinstance(c, BladesClient) or callable(getattr(c, "is_trusted", None)) for c in seq):
             trusted = [i for i, c in enumerate(seq) if c.is_trusted()]
             assert len(trusted) == 1, "FLTrust needs exactly one trusted client"
             return self.aggregate(self._matrix(seq), trusted[0])

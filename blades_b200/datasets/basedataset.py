@@ -53,7 +53,9 @@ class BatchStream:
             if not self._started:
                 from ..utils import set_random_seed
                 set_random_seed(self.seed)
-            self._perm = np.random.permutation(n)
+            # the reference permutes the ALREADY permuted arrays at every epoch (basedataset.py:69-75): compose
+            idx = np.random.permutation(n)
+            self._perm = idx if self._perm is None else self._perm[idx]
         else:
             self._perm = self._rng.permutation(n)
         self._started = True

@@ -246,4 +246,7 @@ def as_matrix(inputs, virtual: Optional[VirtualRows] = None) -> UpdateMatrix:
         return LocalMatrix(torch.stack([c.get_update() for c in inputs]), virtual)
     if len(inputs) and all(torch.is_tensor(e) for e in inputs):
         return LocalMatrix(torch.stack(inputs, dim=0), virtual)
+    if len(inputs) and all(callable(getattr(e, "get_update", None)) for e in inputs):
+        # duck-typed clients (the reference only ever calls ``.get_update()``, mean.py:23)
+        return LocalMatrix(torch.stack([e.get_update() for e in inputs]), virtual)
     raise TypeError("aggregator inputs must be clients, tensors or an UpdateMatrix")
