@@ -4,7 +4,7 @@ import torch.nn as nn
 
 from .core import Tokenizer, TransformerClassifier, register_model
 
-__all__ = ["CCT"]
+__all__ = ["CCT", "cct_2", "cct_4", "cct_6", "cct_7", "cct_14"]
 
 
 class CCT(nn.Module):
