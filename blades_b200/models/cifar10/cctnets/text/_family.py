@@ -40,10 +40,10 @@ class _TextModel(nn.Module):
         return self.classifier(x, mask=mask)
 
 
-def size_factories(cls, prefix, conv_defaults):
+def size_factories(cls, prefix, conv_defaults, sizes=None):
     """``<prefix>_2/_4/_6`` factories; ``conv_defaults(kernel_size) -> (stride, padding)``."""
     out = {}
-    for d, (L, H, R, E) in _SIZES.items():
+    for d, (L, H, R, E) in (sizes or _SIZES).items():
         def f(*args, _L=L, _H=H, _R=R, _E=E, kernel_size=4, stride=None, padding=None, **kwargs):
             extra = {}
             if cls._use_tokenizer:

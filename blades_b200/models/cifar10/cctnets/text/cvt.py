@@ -14,4 +14,6 @@ class TextCVT(_TextModel):
                          *args, **kwargs)
 
 
-globals().update(size_factories(TextCVT, "text_cvt", lambda k: (k, 0)))
+# the reference's text_cvt_6 keeps embedding_dim = 128 (text/cvt.py:71-73), unlike text_cct_6 / text_vit_6 (256)
+_CVT_SIZES = {2: (2, 2, 1, 128), 4: (4, 2, 1, 128), 6: (6, 4, 2, 128)}
+globals().update(size_factories(TextCVT, "text_cvt", lambda k: (k, 0), _CVT_SIZES))
