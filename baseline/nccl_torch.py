@@ -15,9 +15,7 @@ synthetic data generator and the world bootstrap)."""
 from __future__ import annotations
 
 import copy
-import json
 import math
-import tempfile
 import time
 
 import torch

@@ -19,7 +19,7 @@ Each solver returns a weight vector ``w`` such that the aggregate is
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Optional, Tuple
 
 import numpy as np
 

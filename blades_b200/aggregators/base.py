@@ -11,7 +11,6 @@ not touch dense ``[N, d]`` tensors unless they call ``matrix.rows()``.
 """
 from __future__ import annotations
 
-from typing import List, Union
 
 import torch
 

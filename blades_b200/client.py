@@ -18,7 +18,7 @@ from __future__ import annotations
 import copy
 import logging
 from collections import defaultdict
-from typing import Callable, Dict, Iterable, List, Optional, Tuple
+from typing import Callable, Dict, Iterable, Optional, Tuple
 
 import torch
 import torch.nn as nn

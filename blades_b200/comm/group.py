@@ -12,7 +12,7 @@ from __future__ import annotations
 import datetime
 import os
 from dataclasses import dataclass
-from typing import List, Optional, Sequence
+from typing import List, Optional
 
 import numpy as np
 import torch

@@ -1,7 +1,6 @@
 """Federated CIFAR-100 (new; BASELINE config #5 names CIFAR-100/ResNet-50 -- the
 reference ships no CIFAR-100).  Same pipeline as CIFAR10 with 100 classes;
 uneven client splits are allowed so 512 clients work."""
-from typing import Optional
 
 import numpy as np
 

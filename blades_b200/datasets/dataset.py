@@ -8,7 +8,7 @@ whole round's input with a single async H2D copy (the reference does one small
 ``.to(device)`` per batch per client, client.py:186)."""
 from __future__ import annotations
 
-from typing import Iterable, List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 from warnings import warn
 
 import numpy as np

@@ -2,7 +2,6 @@
 equal split (iid) or Dirichlet(alpha) label split."""
 from typing import Optional
 
-import numpy as np
 
 from .basedataset import BaseDataset, partition
 

@@ -31,7 +31,7 @@ import torch.nn as nn
 from ..client import BladesClient, ByzantineClient
 from ..comm.group import World, split_clients
 from ..parallel.matrix import LocalMatrix, UpdateMatrix, VirtualRows
-from ..server import BladesServer, _is_plain_sgd
+from ..server import BladesServer
 from . import batched as cb
 from .flat import FlatParams
 

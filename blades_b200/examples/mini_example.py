@@ -4,7 +4,6 @@
 torchvision; the default is the synthetic MNIST-shaped dataset (no network needed)."""
 import argparse
 
-import torch
 
 from blades_b200 import Simulator
 from blades_b200.comm.group import init_world, shutdown

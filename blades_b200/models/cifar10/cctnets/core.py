@@ -15,7 +15,7 @@ attention-dropout is active, and the explicit softmax path otherwise.
 from __future__ import annotations
 
 import math
-from typing import Callable, Dict, Optional
+from typing import Callable, Dict
 
 import torch
 import torch.nn as nn

@@ -13,7 +13,7 @@ same parameter count) and ``norm='batch_running'`` (stock BN) are available.
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Type
+from typing import Callable, List, Type
 
 import torch
 import torch.nn as nn

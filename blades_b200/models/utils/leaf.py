@@ -8,7 +8,7 @@ import json
 import os
 import random
 from collections import OrderedDict
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, Optional, Tuple
 
 import numpy as np
 

@@ -3,7 +3,7 @@ twin in aggregators/_gramops.py; ``available()`` tells callers whether the nativ
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+from typing import Tuple
 
 import numpy as np
 

@@ -28,7 +28,7 @@ fused kernels never store f identical malicious rows.
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import List, Optional, Sequence, Union
+from typing import Optional, Sequence
 
 import numpy as np
 import torch

@@ -13,7 +13,7 @@ reference only remains as the general fallback (any torch optimizer).
 """
 from __future__ import annotations
 
-from typing import Callable, Optional
+from typing import Callable
 
 import torch
 

@@ -22,7 +22,6 @@ from __future__ import annotations
 
 import importlib
 import logging
-import os
 from time import time
 from typing import Any, Callable, Dict, List, Optional, Union
 
@@ -34,7 +33,7 @@ from .comm.group import World, get_world
 from .datasets.dataset import FLDataset
 from .engine.round import RoundEngine
 from .parallel.matrix import VirtualRows
-from .server import BladesServer, _is_plain_sgd
+from .server import BladesServer
 from .utils import initialize_logger, reset_model_weights, set_random_seed, top1_accuracy
 
 __all__ = ["Simulator"]

@@ -1,5 +1,4 @@
 """Aggregator oracles vs. brute-force definitions (incl. reference quirks)."""
-import math
 
 import numpy as np
 import pytest

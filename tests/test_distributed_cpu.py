@@ -3,7 +3,6 @@ result: client->shard split, row gathering, replicated server state, distributed
 import os
 import socket
 import sys
-import tempfile
 
 import pytest
 import torch

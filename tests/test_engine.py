@@ -1,12 +1,11 @@
 """Engine tests: client-batched fedsgd == time-sliced per-client training; API contract."""
 import copy
 
-import numpy as np
 import pytest
 import torch
 import torch.nn as nn
 
-from blades_b200 import BladesClient, ByzantineClient, Simulator
+from blades_b200 import ByzantineClient, Simulator
 from blades_b200.datasets import synthetic_fldataset
 from blades_b200.engine import batched as cb
 from blades_b200.engine.flat import FlatParams

@@ -3,7 +3,7 @@ import numpy as np
 import torch
 from hypothesis import given, settings, strategies as st
 
-from blades_b200.aggregators import Centeredclipping, Geomed, Krum, Mean, Median, Trimmedmean
+from blades_b200.aggregators import Centeredclipping, Geomed, Mean, Median, Trimmedmean
 from blades_b200.aggregators import _gramops as gops
 from blades_b200.parallel.matrix import LocalMatrix, VirtualRows
 
