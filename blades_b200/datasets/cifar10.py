@@ -14,6 +14,7 @@ __all__ = ["CIFAR10"]
 def _cifar_transforms(mean, std):
     import torchvision.transforms as T
     test = T.Compose([T.Normalize(mean=mean, std=std)])
+    test.deterministic = True          # evaluation may cache the transformed test shards (Simulator.test_actor)
     train = T.Compose([
         T.RandomResizedCrop(32, scale=(0.75, 1.0), ratio=(1.0, 1.0)),
         T.RandomHorizontalFlip(p=0.5),

@@ -345,17 +345,81 @@ class Simulator(object):
         """Evaluate the global model on every client's test shard (length-weighted)."""
         eng = self.engine
         model = self.server.get_model()
-        records = []
-        for gi in eng.local_idx:
-            c = self.get_clients()[gi]
-            data = self.dataset.get_all_test_data(c.id())
-            records.append(c.evaluate(round_number=global_round, test_set=data, batch_size=batch_size,
-                                      metrics=self.metrics, use_actor=True, model=model))
+        records = self._test_batched(global_round, batch_size)
+        if records is None:
+            records = []
+            for gi in eng.local_idx:
+                c = self.get_clients()[gi]
+                data = self.dataset.get_all_test_data(c.id())
+                records.append(c.evaluate(round_number=global_round, test_set=data, batch_size=batch_size,
+                                          metrics=self.metrics, use_actor=True, model=model))
         if self.world.distributed:
             records = [r for part in self.world.all_gather_object(records) for r in part]
         loss, top1 = self.log_validate(records)
         self.debug_logger.info(f"Test global round {global_round}, loss: {loss}, top1: {top1}")
         return loss, top1
+
+    def _test_batched(self, global_round, batch_size):
+        """Evaluation fast path: the reference evaluates client by client in batches of
+        ``batch_size`` (client.py:144-176, ~2 small forwards + 2 host syncs per client).  When the result cannot
+        depend on how samples are grouped -- default top-1 metric, cross-entropy, stock ``evaluate``, test shards
+        without a random per-item transform, no batch-statistics BatchNorm in eval mode -- all local test shards
+        are cached on the device once, pushed through the global model in large chunks, and per-sample loss /
+        correctness are segment-reduced per client: same per-client records, one host sync.  Returns ``None`` when
+        any condition fails (the caller then runs the per-client loop)."""
+        import torch.nn as nn
+        import torch.nn.functional as F
+
+        from .datasets.customdataset import CustomTensorDataset
+        eng = self.engine
+        clients = [self.get_clients()[gi] for gi in eng.local_idx]
+        if not clients or set(self.metrics) != {"top1"} or self.metrics["top1"] is not top1_accuracy:
+            return None
+        if any(type(c).evaluate is not BladesClient.evaluate or not isinstance(c.loss_func, nn.CrossEntropyLoss)
+               for c in clients):
+            return None
+        model = self.server.get_model()
+        if any(isinstance(m, nn.modules.batchnorm._BatchNorm) and not m.track_running_stats for m in model.modules()):
+            return None
+        cache = getattr(self, "_eval_cache", None)
+        if cache is None:
+            xs, ys, lens = [], [], []
+            for c in clients:
+                ds = self.dataset.get_all_test_data(c.id())
+                if not isinstance(ds, CustomTensorDataset):
+                    return None
+                x, y = ds.tensors
+                if ds.transforms is not None:
+                    if not getattr(ds.transforms, "deterministic", False):
+                        return None
+                    x = torch.stack([ds.transforms(xi) for xi in x]) if len(x) else x
+                xs.append(x), ys.append(y), lens.append(len(y))
+            if min(lens) == 0:
+                return None
+            dev = eng.device
+            seg = torch.repeat_interleave(torch.arange(len(lens)), torch.tensor(lens))
+            cache = self._eval_cache = (torch.cat(xs).to(dev), torch.cat(ys).to(dev), seg.to(dev), lens)
+        X, y, seg, lens = cache
+        was_training = model.training
+        model.eval()
+        chunk = max(int(batch_size), 4096)
+        loss_sum = torch.zeros(len(lens), device=X.device, dtype=torch.float64)
+        hit_sum = torch.zeros(len(lens), device=X.device, dtype=torch.float64)
+        with torch.no_grad():
+            for i in range(0, len(y), chunk):
+                out = model(X[i:i + chunk])
+                yy = y[i:i + chunk]
+                loss_sum.index_add_(0, seg[i:i + chunk], F.cross_entropy(out, yy, reduction="none").double())
+                hit_sum.index_add_(0, seg[i:i + chunk], (out.argmax(1) == yy).double())
+        model.train(was_training)
+        stats = torch.stack([loss_sum, hit_sum]).cpu()              # the one host sync
+        records = []
+        for j, c in enumerate(clients):
+            rec = {"_meta": {"type": "client_validation"}, "E": global_round, "Length": lens[j],
+                   "Loss": float(stats[0, j]) / lens[j], "top1": 100.0 * float(stats[1, j]) / lens[j]}
+            c._json_logger.info(rec)
+            records.append(rec)
+        return records
 
     # ------------------------------------------------------------------ logging
     def log_variance(self, cur_round, update):

@@ -255,3 +255,44 @@ def test_channels_last_flat_layout_and_server():
         assert torch.allclose(p1, p2, atol=1e-6)
     x = torch.randn(8, 3, 32, 32)
     assert torch.allclose(m1(x), m2(x), atol=1e-3)
+
+
+def test_batched_evaluation_equals_per_client_loop(tmp_path):
+    """The evaluation fast path produces the per-client records of the reference's client-by-client loop."""
+    import torch
+    from blades_b200 import Simulator
+    from blades_b200.datasets import synthetic_fldataset
+    from blades_b200.models.mnist import MLP
+    ds = synthetic_fldataset(5, shape=(28, 28), num_classes=10, train_bs=8, train_per_client=16, test_per_client=21, seed=2)
+    sim = Simulator(ds, aggregator="mean", use_cuda=False, seed=1, log_path=str(tmp_path / "log"), progress=False)
+    model = MLP()
+    sim.prepare(model, "SGD", "SGD", "crossentropy", 1.0, 0.1)
+    fast = sim._test_batched(3, 8)
+    assert fast is not None and len(fast) == 5
+    slow = [c.evaluate(round_number=3, test_set=sim.dataset.get_all_test_data(c.id()), batch_size=8,
+                       metrics=sim.metrics, model=model) for c in sim.get_clients()]
+    for a, b in zip(fast, slow):
+        assert a["Length"] == b["Length"] == 21 and a["E"] == b["E"] == 3
+        assert abs(a["Loss"] - b["Loss"]) < 1e-5 and abs(a["top1"] - b["top1"]) < 1e-4
+    loss, top1 = sim.test_actor(3, 8)
+    assert abs(loss - sum(r["Loss"] for r in slow) / 5) < 1e-5
+
+
+def test_batched_evaluation_declines_when_grouping_matters(tmp_path):
+    import torch.nn as nn
+    from blades_b200 import Simulator
+    from blades_b200.datasets import synthetic_fldataset
+    from blades_b200.models.mnist import MLP
+    ds = synthetic_fldataset(3, shape=(28, 28), num_classes=10, train_bs=8, train_per_client=16, test_per_client=8, seed=2)
+    # custom metric -> per-client loop
+    sim = Simulator(ds, aggregator="mean", use_cuda=False, seed=1, log_path=str(tmp_path / "a"), progress=False,
+                    metrics={"top1": lambda out, tgt: 0.0})
+    sim.prepare(MLP(), "SGD", "SGD", "crossentropy", 1.0, 0.1)
+    assert sim._test_batched(1, 8) is None
+    # batch-statistics BatchNorm in eval mode -> per-client loop
+    sim = Simulator(ds, aggregator="mean", use_cuda=False, seed=1, log_path=str(tmp_path / "b"), progress=False)
+    net = nn.Sequential(nn.Flatten(), nn.Linear(784, 16), nn.BatchNorm1d(16, track_running_stats=False), nn.Linear(16, 10))
+    sim.prepare(net, "SGD", "SGD", "crossentropy", 1.0, 0.1)
+    assert sim._test_batched(1, 8) is None
+    loss, top1 = sim.test_actor(1, 8)
+    assert loss > 0
