@@ -429,3 +429,111 @@ def test_text_models_match_reference(ref, sub, name, masked):
         assert torch.allclose(got, want, atol=1e-5, rtol=1e-4), L
         return
     pytest.skip("the reference model accepts none of the probed sequence lengths")
+
+
+# ------------------------------------------------------------------------------------------------ A11-A13
+class _Node:
+    def __init__(self, index):
+        self.index, self.edges = index, []
+
+
+class _Edge:
+    def __init__(self, a, b):
+        self.a, self.b = a, b
+        a.edges.append(self), b.edges.append(self)
+
+    def theother(self, n):
+        return self.b if n is self.a else self.a
+
+
+def test_unwired_async_and_decentralized_aggregators_match_reference(ref):
+    """The never-instantiated stubs of the reference exist here with the same semantics."""
+    rmean = ref.import_module("blades.aggregators.mean")
+    rcc = ref.import_module("blades.aggregators.centeredclipping")
+    from blades_b200.aggregators import centeredclipping as occ
+    from blades_b200.aggregators import mean as omean
+    g = torch.Generator().manual_seed(0)
+    vs = [torch.randn(9, generator=g) for _ in range(5)]
+    with_gaps = [vs[0], None, vs[2], vs[3], None]
+    assert torch.allclose(omean._AsyncMean()(with_gaps), rmean._AsyncMean()(with_gaps))
+    r, o = rcc._AsyncCenteredClipping(tau=1.5, n_iter=2), occ._AsyncCenteredClipping(tau=1.5, n_iter=2)
+    for _ in range(3):
+        assert torch.allclose(o(with_gaps), r(with_gaps), atol=1e-6)
+
+    def graph():
+        nodes = [_Node(i) for i in range(3)]
+        _Edge(nodes[0], nodes[1]), _Edge(nodes[0], nodes[2])
+        return nodes
+    w = torch.tensor([0.5, 0.3, 0.2])
+    nr, no = graph(), graph()
+    want = rmean._DecentralizedAggregator(nr[0], w)([v.clone() for v in vs[:3]])
+    got = omean._DecentralizedAggregator(no[0], w)([v.clone() for v in vs[:3]])
+    assert torch.allclose(got, want)
+
+    def anchor(mod, nodes):
+        torch.manual_seed(3)
+        net = torch.nn.Linear(4, 2)
+        opt = torch.optim.SGD(net.parameters(), lr=0.1)
+        agg = mod._AnchorClipping(nodes[0], w, opt, net, tau=0.7, n_iter=1)
+        outs = []
+        d = sum(p.numel() for p in net.parameters())
+        for step in range(2):
+            ins = [torch.randn(d, generator=torch.Generator().manual_seed(10 * step + j)) for j in range(3)]
+            outs.append(agg(ins))
+            net(torch.ones(1, 4)).sum().backward()
+            opt.step()                      # the wrapped step moves the anchor
+        return outs
+    for a, b in zip(anchor(occ, graph()), anchor(rcc, graph())):
+        assert torch.allclose(a, b, atol=1e-6)
+
+
+def test_byzantinesgd_matches_reference(ref):
+    rmod = ref.import_module("blades.aggregators.byzantinesgd")
+    from blades_b200.aggregators.byzantinesgd import ByzantineSGD
+
+    def run(cls):
+        torch.manual_seed(1)
+        net = torch.nn.Linear(6, 3)
+        opt = torch.optim.SGD(net.parameters(), lr=0.05)
+        agg = cls(m=7, th_A=50.0, th_B=60.0, th_V=8.0, optimizer=opt)
+        d = sum(p.numel() for p in net.parameters())
+        outs = []
+        for step in range(3):
+            g = torch.Generator().manual_seed(100 + step)
+            grads = [torch.randn(d, generator=g) for _ in range(7)]
+            grads[0] = grads[0] + 30.0                     # one outlier the filter must drop
+            out = agg(grads)
+            outs.append(out.clone())
+            with torch.no_grad():                          # move the model so A_i accumulates something
+                for p in net.parameters():
+                    p.add_(0.01)
+        return outs, sorted(agg.good)
+    (want, good_r), (got, good_o) = run(rmod.ByzantineSGD), run(ByzantineSGD)
+    assert good_r == good_o and 0 not in good_o
+    for a, b in zip(got, want):
+        assert torch.allclose(a.double(), b.double(), atol=1e-5)
+
+
+def test_torch_utils_match_reference(ref):
+    rtu = ref.import_module("blades.aggregators.torch_utils")
+    from blades_b200.aggregators import torch_utils as otu
+    g = torch.Generator().manual_seed(0)
+    for max_norm in (0.5, 100.0):
+        a = [torch.randn(20, generator=g) * 3]
+        b = [a[0].clone()]
+        rtu.clip_tensor_norm_(a, max_norm=max_norm)
+        otu.clip_tensor_norm_(b, max_norm=max_norm)
+        assert torch.allclose(a[0], b[0])
+    d1 = {"w": torch.randn(4, 5, generator=g) * 2, "b": torch.randn(4, generator=g), "steps": torch.tensor([3])}
+    d2 = {k: v.clone() for k, v in d1.items()}
+    want = rtu.clip_para_norm_(d1, max_norm=0.3)              # state-dict in, clipped in place, int64 entries skipped
+    got = otu.clip_para_norm_(d2, max_norm=0.3)
+    assert abs(float(want) - float(got)) < 1e-6
+    assert all(torch.allclose(d1[k].double(), d2[k].double()) for k in d1)
+    s1 = {"w": torch.randn(3, 3, generator=g), "b": torch.randn(3, generator=g)}
+    s2 = {"w": torch.randn(3, 3, generator=g), "b": torch.randn(3, generator=g)}
+    for fn in ("l2dist", "cos_sim"):
+        assert abs(float(getattr(rtu, fn)(s1, s2)) - float(getattr(otu, fn)(s1, s2))) < 1e-6
+    assert abs(float(rtu.l2norm(s1)) - float(otu.l2norm(s1))) < 1e-6
+    x = torch.randn(4, 7, generator=g)
+    assert torch.allclose(rtu.HLoss()(x), otu.HLoss()(x))
