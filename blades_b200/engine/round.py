@@ -453,9 +453,11 @@ class RoundEngine:
                     agg = aggregate_fn()
                 mat = matrix_fn()
                 ok = mat is not None and mat.step_applied
-            except Exception:
+            except Exception as e:     # capture is an optimisation: fall back to eager rounds, but say so
                 ok = False
                 torch.cuda.synchronize(self.device)
+                import logging
+                logging.getLogger("debug").warning(f"whole-round CUDA graph capture failed, running eagerly: {e!r}")
             n_native = _loader.LAUNCHES - before
             _loader.count_launch(-n_native)
             if not ok:
