@@ -147,7 +147,12 @@ class FLDataset:
                 out[u] = s.state()
         return out
 
+    def stream_state(self, u_id):
+        """Cursor of one client's stream (``None`` when the stream is not resumable)."""
+        s = self._train_dls.get(u_id)
+        return s.state() if hasattr(s, "state") else None
+
     def load_state_dict(self, state: dict) -> None:
         for u, st in state.items():
-            if hasattr(self._train_dls.get(u), "load_state"):
+            if st is not None and hasattr(self._train_dls.get(u), "load_state"):
                 self._train_dls[u].load_state(st)

@@ -123,10 +123,13 @@ class RoundEngine:
         self._zc_plans = {}
         self._pf_jobs = {}
         self._pf_deferred = None
-        self._pf_last = None
-        self._cursor_after = {}
+        self._pf_slot_of = {}       # request key -> next slot (0/1)
+        self._pf_keyidx = {}        # request key -> index (names the pinned staging buffers)
+        self._pf_pre = {}           # request key -> {client id: cursor before its unconsumed prefetched batch}
         self.track_cursors = False
         import os
+        #: exercise the worker-thread prefetcher without a GPU (tests)
+        self.prefetch_on_cpu = os.environ.get("BLADES_PREFETCH_CPU", "0") == "1"
         self.prefetch = os.environ.get("BLADES_PREFETCH", "1") != "0"
         #: clients per fused forward/backward (0 = all local clients at once)
         self.max_batched_clients = int(os.environ.get("BLADES_MAX_BATCHED_CLIENTS", "0"))
@@ -210,30 +213,38 @@ class RoundEngine:
 
     # -- batched fedsgd ------------------------------------------------------------
     def stage_batches(self, rows: Optional[Sequence[int]] = None, num_batches: int = 1):
-        """This round's inputs on the device.  Host batch assembly (multi-threaded C++ gather into pinned
-        memory) and the H2D copy of round r+1 run on a worker thread + copy stream WHILE round r computes
-        (double-buffered pinned and device staging buffers, event-ordered); the reference does one blocking
-        ``.to(device)`` per batch per client inside the training loop (client.py:186)."""
+        """This round's inputs on the device.  The inputs of round r+1 are produced WHILE round r computes, into
+        per-request double buffers ordered by events: either the zero-copy gather kernel reads the selected
+        samples straight from the pinned host shards (``_zero_copy_submit``), or a worker thread assembles the
+        batches (multi-threaded C++ gather into pinned staging) and copies them H2D on a side stream.  The
+        reference does one blocking ``.to(device)`` per batch per client inside the training loop (client.py:186).
+
+        A "request" is one ``(rows, num_batches)`` key -- with ``max_batched_clients`` chunking there are several
+        per round; every key owns its two slots, so the prefetch of one chunk can never land in a buffer another
+        chunk has not consumed yet."""
         rows = list(range(len(self.local_idx))) if rows is None else list(rows)
-        if self.device.type != "cuda" or not self.prefetch:
+        on_cuda = self.device.type == "cuda"
+        if not self.prefetch or not (on_cuda or self.prefetch_on_cpu):
             X, y = self._assemble(rows, num_batches, 0)
             self.h2d_bytes = X.numel() * X.element_size() + y.numel() * y.element_size()
-            nb = self.device.type == "cuda"
-            return X.to(self.device, non_blocking=nb), y.to(self.device, non_blocking=nb)
+            return X.to(self.device, non_blocking=on_cuda), y.to(self.device, non_blocking=on_cuda)
         key = (tuple(rows), num_batches)
         self.flush_prefetch()
         fut = self._pf_jobs.pop(key, None)
         if fut is None:
             fut = self._pf_submit(rows, num_batches)
         X, y, ev, slot = fut.result()
-        torch.cuda.current_stream(self.device).wait_event(ev)
+        self._pf_pre.pop(key, None)                      # that batch is consumed now
+        consumed = None
+        if on_cuda:
+            torch.cuda.current_stream(self.device).wait_event(ev)
         self.h2d_bytes = X.numel() * X.element_size() + y.numel() * y.element_size()
-        # consumers enqueue their reads right after this call; the slot may be refilled two rounds later.
-        # The request for round r+1 is issued by flush_prefetch() AFTER this round's work has been launched
-        # (its host part then overlaps the GPU), but ordered against the reads enqueued so far.
-        self._pf_last = (key, slot)
-        consumed = torch.cuda.Event()
-        consumed.record(torch.cuda.current_stream(self.device))
+        # The request for round r+1 is issued by flush_prefetch() AFTER this round's work has been launched (its
+        # host part then overlaps the GPU).  It refills the key's OTHER slot, last read one round ago: everything
+        # enqueued on the main stream up to here is a safe (conservative) ordering point for that refill.
+        if on_cuda:
+            consumed = torch.cuda.Event()
+            consumed.record(torch.cuda.current_stream(self.device))
         self._pf_deferred = (key, rows, num_batches, consumed)
         return X, y
 
@@ -248,34 +259,55 @@ class RoundEngine:
         ids = [self.clients[self.local_idx[r]].id() for r in rows]
         return self.dataset.get_train_batches(ids, num_batches, slot=slot)
 
+    def _next_slot(self, key) -> int:
+        """Each request key alternates between its own two slots."""
+        s = self._pf_slot_of.get(key, 0)
+        self._pf_slot_of[key] = s ^ 1
+        return s
+
+    def _snapshot_cursors(self, key, rows) -> None:
+        """Per-client stream cursors right BEFORE the batches of a prefetch are drawn: what a checkpoint must
+        store for these clients while that prefetched batch is still unconsumed (``data_cursors``)."""
+        if self.track_cursors and hasattr(self.dataset, "stream_state"):
+            self._pf_pre[key] = {self.clients[self.local_idx[r]].id():
+                                 self.dataset.stream_state(self.clients[self.local_idx[r]].id()) for r in rows}
+
     def _pf_submit(self, rows, num_batches, consumed=None):
         import concurrent.futures as cf
-        zc = self._zero_copy_submit(rows, num_batches, consumed)
-        if zc is not None:
-            return zc
+        on_cuda = self.device.type == "cuda"
+        key = (tuple(rows), num_batches)
+        if on_cuda:
+            zc = self._zero_copy_submit(rows, num_batches, consumed)
+            if zc is not None:
+                return zc
         if self._pf_pool is None:
             self._pf_pool = cf.ThreadPoolExecutor(max_workers=1, thread_name_prefix="blades-prefetch")
-            if self._pf_stream is None:
-                self._pf_stream = torch.cuda.Stream(device=self.device)
-                self._pf_slot = 0
             self._pf_dev = {}
-        slot = self._pf_slot
-        self._pf_slot ^= 1
-        # the device staging buffer of this slot was last read by work enqueued on the main stream
-        if consumed is None:
+        if on_cuda and self._pf_stream is None:
+            self._pf_stream = torch.cuda.Stream(device=self.device)
+        slot = self._next_slot(key)
+        # pinned staging buffers of the dataset are keyed by an integer: unique per (key, slot); ids >= 100 belong
+        # to the fedavg worker replicas
+        staging = 2 * self._pf_keyidx.setdefault(key, len(self._pf_keyidx)) + slot
+        if staging >= 100:
+            raise RuntimeError("too many distinct prefetch requests per round; set BLADES_PREFETCH=0")
+        if on_cuda and consumed is None:
             consumed = torch.cuda.Event()
             consumed.record(torch.cuda.current_stream(self.device))
 
         def job():
-            torch.cuda.set_device(self.device)
-            X, y = self._assemble(rows, num_batches, slot)
-            if self.track_cursors:
-                self._cursor_after[slot] = self.dataset.state_dict()
-            bufs = self._pf_dev.get((slot, tuple(X.shape)))
-            if bufs is None:
-                bufs = self._pf_dev[(slot, tuple(X.shape))] = (
-                    torch.empty(X.shape, dtype=X.dtype, device=self.device),
-                    torch.empty(y.shape, dtype=y.dtype, device=self.device))
+            if on_cuda:
+                torch.cuda.set_device(self.device)
+            self._snapshot_cursors(key, rows)
+            X, y = self._assemble(rows, num_batches, staging)
+            bufs = self._pf_dev.get((key, slot))
+            if bufs is None or bufs[0].shape != X.shape:
+                bufs = self._pf_dev[(key, slot)] = (torch.empty(X.shape, dtype=X.dtype, device=self.device),
+                                                    torch.empty(y.shape, dtype=y.dtype, device=self.device))
+            if not on_cuda:
+                bufs[0].copy_(X)
+                bufs[1].copy_(y)
+                return bufs[0], bufs[1], None, slot
             with torch.cuda.stream(self._pf_stream):
                 self._pf_stream.wait_event(consumed)
                 bufs[0].copy_(X, non_blocking=True)
@@ -312,21 +344,18 @@ class RoundEngine:
                 idx_done=[None, None])
             if self._pf_stream is None:
                 self._pf_stream = torch.cuda.Stream(device=self.device)
-                self._pf_slot = 0
         elif plan is False:
             return None
         from ..ops import gather as kg
-        slot = self._pf_slot
-        self._pf_slot ^= 1
+        slot = self._next_slot(key)
         if plan["idx_done"][slot] is not None:
             plan["idx_done"][slot].synchronize()         # the pinned index buffer of this slot is free again
+        self._snapshot_cursors(key, rows)
         h = plan["h_idx"][slot].numpy().reshape(plan["n"], plan["per"])
         bs = plan["bs"]
         for i, st in enumerate(plan["streams"]):
             for j in range(plan["per"] // bs):
                 h[i, j * bs:(j + 1) * bs] = st.next_indices()
-        if self.track_cursors:
-            self._cursor_after[slot] = self.dataset.state_dict()
         if consumed is None:
             consumed = torch.cuda.Event()
             consumed.record(torch.cuda.current_stream(self.device))
@@ -350,10 +379,17 @@ class RoundEngine:
         return _Done((plan["X"][slot], plan["y"][slot], ev, slot))
 
     def data_cursors(self):
-        """Data-stream cursors as of the batches consumed so far (the prefetcher runs one round ahead)."""
-        if self._pf_last is not None and self.track_cursors and self._pf_last[1] in self._cursor_after:
-            return self._cursor_after[self._pf_last[1]]
-        return self.dataset.state_dict() if hasattr(self.dataset, "state_dict") else {}
+        """Data-stream cursors as of the batches CONSUMED so far.  The prefetcher runs one round ahead: for every
+        request whose prefetched batch is still unconsumed, its clients' cursors are the ones snapshotted right
+        before that batch was drawn."""
+        if not hasattr(self.dataset, "state_dict"):
+            return {}
+        for fut in list(self._pf_jobs.values()):
+            fut.result()                                 # let in-flight draws finish before reading the streams
+        cur = self.dataset.state_dict()
+        for pre in list(self._pf_pre.values()):
+            cur.update(pre)
+        return cur
 
     def _graph_eligible(self, rows: List[int]) -> bool:
         """CUDA-graph replay of the batched step needs every hook to be a pure device-tensor function:

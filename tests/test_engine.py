@@ -296,3 +296,47 @@ def test_batched_evaluation_declines_when_grouping_matters(tmp_path):
     assert sim._test_batched(1, 8) is None
     loss, top1 = sim.test_actor(1, 8)
     assert loss > 0
+
+
+@pytest.mark.parametrize("chunk", [0, 2, 3])
+def test_prefetcher_with_chunked_requests_matches_synchronous_staging(tmp_path, monkeypatch, chunk):
+    """The one-round-ahead prefetcher (worker thread, per-request double buffers) feeds exactly the batches the
+    synchronous path would, also when ``max_batched_clients`` splits a round into several requests."""
+    def run(prefetch_cpu):
+        monkeypatch.setenv("BLADES_PREFETCH_CPU", "1" if prefetch_cpu else "0")
+        monkeypatch.setenv("BLADES_MAX_BATCHED_CLIENTS", str(chunk))
+        ds = synthetic_fldataset(6, shape=(28, 28), num_classes=10, train_bs=8, train_per_client=24, test_per_client=8, seed=4)
+        sim = Simulator(ds, num_byzantine=2, attack="ipm", aggregator="median", log_path=str(tmp_path / f"l{prefetch_cpu}"),
+                        seed=1, progress=False)
+        torch.manual_seed(0)
+        m = MLP()
+        sim.run(m, global_rounds=7, local_steps=1, server_lr=1.0, client_lr=0.1, validate_interval=100)
+        assert sim.engine.prefetch_on_cpu == prefetch_cpu
+        if prefetch_cpu:
+            assert len(sim.engine._pf_slot_of) == (1 if chunk == 0 else -(-6 // chunk))
+        return torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+    assert torch.equal(run(True), run(False))
+
+
+def test_checkpoint_resume_is_exact_with_prefetch_and_chunking(tmp_path, monkeypatch):
+    """The prefetcher has already drawn round r+1's batches when round r is checkpointed: the stored cursors must be
+    the ones before those draws, for every chunk's clients."""
+    monkeypatch.setenv("BLADES_PREFETCH_CPU", "1")
+    monkeypatch.setenv("BLADES_MAX_BATCHED_CLIENTS", "2")
+    ck = str(tmp_path / "ck.pt")
+    ds_args = dict(shape=(28, 28), num_classes=10, train_bs=8, train_per_client=24, test_per_client=8, seed=5)
+
+    def make(tag):
+        return Simulator(synthetic_fldataset(6, **ds_args), aggregator="trimmedmean", aggregator_kws={"nb": 1},
+                         log_path=str(tmp_path / tag), seed=1, progress=False)
+    kw = dict(local_steps=1, server_lr=1.0, client_lr=0.1, validate_interval=100)
+    torch.manual_seed(0)
+    m = MLP()
+    make("a").run(m, global_rounds=6, **kw)
+    final = torch.cat([p.detach().reshape(-1) for p in m.parameters()]).clone()
+    torch.manual_seed(0)
+    ma = MLP()
+    make("b").run(ma, global_rounds=3, checkpoint_path=ck, checkpoint_interval=3, **kw)
+    mb = MLP()
+    make("c").run(mb, global_rounds=6, resume=ck, **kw)
+    assert torch.allclose(torch.cat([p.detach().reshape(-1) for p in mb.parameters()]), final, atol=1e-7)

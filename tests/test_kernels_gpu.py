@@ -516,3 +516,27 @@ def test_zero_copy_input_path_equals_host_path(monkeypatch):
     b, used_b = run("0")
     assert used_a and not used_b
     assert torch.equal(a, b)
+
+
+def test_prefetch_with_chunked_requests_on_gpu(monkeypatch, tmp_path):
+    """``max_batched_clients`` splits a round into several prefetch requests: zero-copy gather, worker-thread staging
+    and synchronous staging must all feed the same batches (every request owns its two slots)."""
+    from blades_b200 import Simulator
+    from blades_b200.datasets import synthetic_fldataset
+    from blades_b200.models.mnist import MLP
+
+    def run(zero_copy, prefetch):
+        monkeypatch.setenv("BLADES_ZERO_COPY", zero_copy)
+        monkeypatch.setenv("BLADES_PREFETCH", prefetch)
+        monkeypatch.setenv("BLADES_MAX_BATCHED_CLIENTS", "2")
+        ds = synthetic_fldataset(8, shape=(28, 28), num_classes=10, train_bs=16, train_per_client=64,
+                                 test_per_client=16, seed=3)
+        sim = Simulator(ds, num_byzantine=2, attack="ipm", aggregator="median", use_cuda=True, seed=3,
+                        log_path=str(tmp_path / f"l{zero_copy}{prefetch}"), progress=False)
+        torch.manual_seed(0)
+        m = MLP()
+        sim.run(model=m, global_rounds=6, local_steps=1, client_lr=0.1, server_lr=1.0, validate_interval=100)
+        return sim.engine.gflat.theta.clone()
+    ref = run("0", "0")
+    assert torch.equal(run("1", "1"), ref)
+    assert torch.equal(run("0", "1"), ref)
