@@ -250,8 +250,13 @@ def run_reference(args) -> dict:
             "global_batch": n_clients * args.batch, "seq_len": None,
             "parallelism": f"{max(1, args.gpus)} actor(s), one per GPU (ray API shim: in-process actor threads, "
                            "no object-store pickling -- cheaper than real Ray)"},
-        "e2e": {"value": r["value"], "unit": "rounds/s", "note": "the reference has one path: host batches -> "
-                "per-client .to(device) -> train -> updates to CPU -> CPU aggregation; its wall clock IS end to end"},
+        "e2e": {"value": r["value"], "unit": "rounds/s",
+                # derived from the reference's code path, not instrumented: per client per round the batch and the
+                # model go H2D (client.py:124,186) and the flat parameters come back twice (client.py:216-228)
+                "h2d_bytes_per_step": n_clients * (args.batch * (3 * 32 * 32 * 4 + 8) + 11181642 * 4),
+                "d2h_bytes_per_step": n_clients * 2 * 11181642 * 4,
+                "note": "the reference has one path: host batches -> per-client .to(device) -> train -> updates "
+                        "to CPU -> CPU aggregation; its wall clock IS end to end"},
         "gpu_launches": 0, "requested": r["requested"], "round_s": r["round_s"], "note": r.get("note", ""),
     }
 
