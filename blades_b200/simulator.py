@@ -524,7 +524,12 @@ class Simulator(object):
                 if server_lr_scheduler:
                     server_lr_scheduler.step()
                 if client_lr_scheduler:
-                    client_lr_scheduler.step()
+                    import warnings
+                    with warnings.catch_warnings():
+                        # the client schedule is a user-owned scheduler on a dummy optimizer that never steps
+                        # (reference scripts/cifar10.py:43-46): torch's ordering warning does not apply
+                        warnings.filterwarnings("ignore", message="Detected call of `lr_scheduler.step\\(\\)` before")
+                        client_lr_scheduler.step()
                     client_lr = client_lr_scheduler.get_last_lr()[0]
                 if self.device.type == "cuda":
                     torch.cuda.synchronize(self.device)
