@@ -199,7 +199,9 @@ def run_ours(args) -> dict:
     if e2e_ms is not None:
         out["e2e"] = {"value": args.steps / (e2e_ms / 1e3), "unit": "rounds/s", "ms_per_step": e2e_ms / args.steps,
                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                      "round_ms_median_rank0": sorted(per_round)[len(per_round) // 2], "round_ms_max_rank0": max(per_round)}
+                      "round_ms_median_rank0": sorted(per_round)[len(per_round) // 2], "round_ms_max_rank0": max(per_round),
+                      "h2d_mechanism": ("gather kernel reading the pinned host shards over PCIe (zero-copy) + index upload"
+                                        if any(eng._zc_plans.values()) else "pinned staging buffer + cudaMemcpyAsync")}
     return out if world.rank == 0 else {}
 
 

@@ -239,6 +239,8 @@ class RoundEngine:
         if on_cuda:
             torch.cuda.current_stream(self.device).wait_event(ev)
         self.h2d_bytes = X.numel() * X.element_size() + y.numel() * y.element_size()
+        if self._zc_plans.get(key):
+            self.h2d_bytes += y.numel() * 8              # zero-copy path: the index list is uploaded as well
         # The request for round r+1 is issued by flush_prefetch() AFTER this round's work has been launched (its
         # host part then overlaps the GPU).  It refills the key's OTHER slot, last read one round ago: everything
         # enqueued on the main stream up to here is a safe (conservative) ordering point for that refill.
