@@ -159,7 +159,7 @@ def run_ours(args) -> dict:
     h2d = d2h = 0
     e2e_ms = None
     if not args.no_e2e:
-        for r in range(min(args.warmup, 3)):
+        for r in range(max(args.warmup, 10)):       # untimed: also absorbs one-off host stalls after the phase switch
             one_round(r)
             float(eng.last_client_losses.mean()) if eng.last_client_losses is not None else None
         torch.cuda.synchronize()
