@@ -14,6 +14,7 @@
 
 #define CE(a, b) { float lo_ = fminf(v[a], v[b]); v[b] = fmaxf(v[a], v[b]); v[a] = lo_; }
 #include "gen/sortnet_gen.cuh"
+#include "select_part_core.cuh"
 #undef CE
 
 struct SelectParams {
@@ -125,6 +126,30 @@ coord_select_kernel(const __grid_constant__ SelectParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Partition-only trimmed mean (select_part_core.cuh): n_real == NP == 4 * trim_b and (no virtual rows or f >= b)
+// -- the "20 % attackers, Trimmedmean(nb = f)" family (N = 20k clients: 16k honest rows, b = 4k).  Two half-size
+// sorts + two bitonic splits instead of one full network: ~21 % fewer FMNMX on the pipe that bounds this kernel.
+template <int NP>
+__global__ void __launch_bounds__(SelectBlock<NP>::kMax)
+coord_select_part_kernel(const __grid_constant__ SelectParams p) {
+    const long long c = p.c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.c1) return;
+    constexpr int H = NP / 2;
+    float a[H], b[H];
+    const unsigned cu = (unsigned)c;
+#pragma unroll
+    for (int i = 0; i < H; ++i) a[i] = __ldcs(p.rows[i] + cu);
+#pragma unroll
+    for (int i = 0; i < H; ++i) b[i] = __ldcs(p.rows[H + i] + cu);
+#pragma unroll
+    for (int i = 0; i < H; ++i) { a[i] = bl_sanitize(a[i]); b[i] = bl_sanitize(b[i]); }
+    const int f = p.n_virtual;
+    float m = 0.f;
+    if (f > 0) m = bl_virtual_value<NP>(a, b, p.n_stat, p.virt_kind, p.virt_param);
+    bl_epilogue_store(p.ep, c, bl_trimmed_partition<NP>(a, b, m, f));
+}
+
+// ---------------------------------------------------------------------------------------------
 // Large-N fallback (128 < N <= 512): a block sorts a [NP x 32-coordinate] tile in shared memory
 // with a bitonic network (one __syncthreads per stage).  Virtual rows are materialised into the
 // tile (value computed per coordinate first).
@@ -204,6 +229,23 @@ static int select_block_size(int kmax) {
     return (b / 32) * 32;
 }
 
+static bool select_partition_enabled() {
+    static const bool on = [] { const char* e = getenv("BLADES_SELECT_PARTITION"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+template <int NP>
+static bool launch_partition(const SelectParams& p, unsigned grid, int block, cudaStream_t st) {
+    if constexpr (NP % 16 == 0) {
+        if (p.mode == 0 && p.n_real == NP && p.trim_b * 4 == NP && (p.n_virtual == 0 || p.n_virtual >= p.trim_b)
+            && (p.n_virtual == 0 || p.n_stat >= 2 || p.virt_kind != 1) && select_partition_enabled()) {
+            coord_select_part_kernel<NP><<<grid, block, 0, st>>>(p);
+            return true;
+        }
+    }
+    return false;
+}
+
 template <int NP>
 static cudaError_t launch_small(const SelectParams& p, cudaStream_t st) {
     const long long cols = p.c1 - p.c0;
@@ -211,6 +253,7 @@ static cudaError_t launch_small(const SelectParams& p, cudaStream_t st) {
     if (p.c1 > 0xFFFFFFFFLL) return cudaErrorInvalidValue;      // 32-bit element offsets
     const int block = select_block_size(SelectBlock<NP>::kMax);
     const unsigned grid = (unsigned)((cols + block - 1) / block);
+    if (launch_partition<NP>(p, grid, block, st)) return cudaGetLastError();
     if (p.mode == 0) coord_select_kernel<NP, 0><<<grid, block, 0, st>>>(p);
     else coord_select_kernel<NP, 1><<<grid, block, 0, st>>>(p);
     return cudaGetLastError();

@@ -540,3 +540,39 @@ def test_prefetch_with_chunked_requests_on_gpu(monkeypatch, tmp_path):
     ref = run("0", "0")
     assert torch.equal(run("1", "1"), ref)
     assert torch.equal(run("0", "1"), ref)
+
+
+@pytest.mark.parametrize("n,b", [(16, 4), (32, 8), (64, 16), (80, 20), (128, 32)])
+def test_trimmed_mean_partition_kernel(n, b, monkeypatch):
+    """n real rows = 4b: the partition-only kernel (two half sorts + bitonic splits) equals the sort reference and
+    the generic full-network kernel, with outliers larger than everything else among the trimmed rows."""
+    from blades_b200.ops import select
+    d = 30011
+    U = torch.randn(n, d, device=_dev())
+    U[0, :7] = float("nan")
+    U[1, 7:11] = float("inf")
+    U[: b // 2] += 1e6                                   # huge rows that must be trimmed without cancellation
+    ref = _trim_ref(torch.nan_to_num(U), b)
+    out = select.trimmed_mean(U, b)
+    assert torch.allclose(out, ref, atol=1e-5, rtol=1e-5), (out - ref).abs().max()
+
+
+@pytest.mark.parametrize("kind,param", [("alie", 0.2858), ("ipm", 2.0)])
+@pytest.mark.parametrize("R,f,b,stat_less", [(20, 4, 4, 0), (40, 8, 8, 0), (100, 20, 20, 0), (60, 12, 12, 3), (100, 25, 20, 0)])
+def test_trimmed_mean_partition_kernel_with_virtual_rows(kind, param, R, f, b, stat_less):
+    """R client rows, the first f of them virtual ALIE/IPM rows (f >= b) merged analytically; R - f = 4b real rows
+    take the partition kernel (the last case, 75 real rows, is the generic-kernel control).  ``stat_less`` further
+    Byzantine clients keep their real rows but are excluded from the attack statistics."""
+    from blades_b200.ops import select
+    from blades_b200.parallel.matrix import VirtualRows
+    d = 20011
+    U = torch.randn(R, d, device=_dev()) * 0.01
+    byz = list(range(f + stat_less))
+    v = VirtualRows(kind, param, list(range(f)), byzantine=byz)
+    honest = U[f + stat_less:].double()
+    val = honest.mean(0) - param * honest.std(0) if kind == "alie" else -param * honest.mean(0)
+    Um = U.clone()
+    Um[:f] = val.float()
+    out = select.trimmed_mean(U, b, virtual=v)
+    ref = _trim_ref(Um, b)
+    assert torch.allclose(out, ref, atol=1e-6, rtol=1e-4), (out - ref).abs().max()
