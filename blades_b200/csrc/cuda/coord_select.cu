@@ -127,7 +127,7 @@ coord_select_kernel(const __grid_constant__ SelectParams p) {
 
 // ---------------------------------------------------------------------------------------------
 // Partition-only trimmed mean (select_part_core.cuh): n_real == NP == 4 * trim_b and (no virtual rows or f >= b)
-// -- the "20 % attackers, Trimmedmean(nb = f)" family (N = 20k clients: 16k honest rows, b = 4k).  Two half-size
+// -- the "20 % attackers, Trimmedmean(nb = f)" family (N = 10k clients: 8k honest rows, b = 2k).  Two half-size
 // sorts + two bitonic splits instead of one full network: ~21 % fewer FMNMX on the pipe that bounds this kernel.
 template <int NP>
 __global__ void __launch_bounds__(SelectBlock<NP>::kMax)
@@ -236,7 +236,7 @@ static bool select_partition_enabled() {
 
 template <int NP>
 static bool launch_partition(const SelectParams& p, unsigned grid, int block, cudaStream_t st) {
-    if constexpr (NP % 16 == 0) {
+    if constexpr (NP % 8 == 0) {
         if (p.mode == 0 && p.n_real == NP && p.trim_b * 4 == NP && (p.n_virtual == 0 || p.n_virtual >= p.trim_b)
             && (p.n_virtual == 0 || p.n_stat >= 2 || p.virt_kind != 1) && select_partition_enabled()) {
             coord_select_part_kernel<NP><<<grid, block, 0, st>>>(p);

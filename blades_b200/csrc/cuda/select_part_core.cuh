@@ -50,7 +50,7 @@ BL_CORE_FN float bl_virtual_value(const float (&a)[NP / 2], const float (&b)[NP 
 // Destroys a and b (sorted in place).
 template <int NP>
 BL_CORE_FN float bl_trimmed_partition(float (&a)[NP / 2], float (&b)[NP / 2], float m, int f) {
-    static_assert(NP % 16 == 0 && NP >= 16 && NP <= 128, "halves must be SortNet sizes");
+    static_assert(NP % 8 == 0 && NP >= 8 && NP <= 128, "halves must be SortNet sizes (multiples of 4)");
     constexpr int H = NP / 2, Q = NP / 4;
     SortNet<H>::run(a);
     SortNet<H>::run(b);

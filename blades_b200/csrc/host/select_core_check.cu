@@ -72,7 +72,8 @@ static void run(std::mt19937& rng) {
 
 int main() {
     std::mt19937 rng(12345);
-    run<16>(rng); run<32>(rng); run<48>(rng); run<64>(rng); run<80>(rng); run<96>(rng); run<112>(rng); run<128>(rng);
+    run<8>(rng); run<16>(rng); run<24>(rng); run<32>(rng); run<40>(rng); run<48>(rng); run<56>(rng); run<64>(rng);
+    run<72>(rng); run<80>(rng); run<88>(rng); run<96>(rng); run<104>(rng); run<112>(rng); run<120>(rng); run<128>(rng);
     std::printf("%d cases, %d failures\n", g_cases, g_fail);
     return g_fail ? 1 : 0;
 }

@@ -542,7 +542,7 @@ def test_prefetch_with_chunked_requests_on_gpu(monkeypatch, tmp_path):
     assert torch.equal(run("0", "1"), ref)
 
 
-@pytest.mark.parametrize("n,b", [(16, 4), (32, 8), (64, 16), (80, 20), (128, 32)])
+@pytest.mark.parametrize("n,b", [(8, 2), (16, 4), (24, 6), (32, 8), (40, 10), (64, 16), (80, 20), (104, 26), (128, 32)])
 def test_trimmed_mean_partition_kernel(n, b, monkeypatch):
     """n real rows = 4b: the partition-only kernel (two half sorts + bitonic splits) equals the sort reference and
     the generic full-network kernel, with outliers larger than everything else among the trimmed rows."""
@@ -558,7 +558,7 @@ def test_trimmed_mean_partition_kernel(n, b, monkeypatch):
 
 
 @pytest.mark.parametrize("kind,param", [("alie", 0.2858), ("ipm", 2.0)])
-@pytest.mark.parametrize("R,f,b,stat_less", [(20, 4, 4, 0), (40, 8, 8, 0), (100, 20, 20, 0), (60, 12, 12, 3), (100, 25, 20, 0)])
+@pytest.mark.parametrize("R,f,b,stat_less", [(10, 2, 2, 0), (20, 4, 4, 0), (40, 8, 8, 0), (50, 10, 10, 0), (100, 20, 20, 0), (60, 12, 12, 3), (100, 25, 20, 0)])
 def test_trimmed_mean_partition_kernel_with_virtual_rows(kind, param, R, f, b, stat_less):
     """R client rows, the first f of them virtual ALIE/IPM rows (f >= b) merged analytically; R - f = 4b real rows
     take the partition kernel (the last case, 75 real rows, is the generic-kernel control).  ``stat_less`` further

@@ -1,6 +1,6 @@
 """The partition-only trimmed-mean core of the GPU kernel (csrc/cuda/select_part_core.cuh + the generated sorting
-networks) is compiled for the HOST and checked against a sort-based double-precision reference: 12 800 cases over
-NP = 16..128, f in {0, Q, Q+1, 2Q+5}, ALIE / IPM virtual values, ties, constants and 1e6 outliers.  No GPU needed --
+networks) is compiled for the HOST and checked against a sort-based double-precision reference: 25 600 cases over
+NP = 8..128, f in {0, Q, Q+1, 2Q+5}, ALIE / IPM virtual values, ties, constants and 1e6 outliers.  No GPU needed --
 the same source files are what nvcc compiles into coord_select_part_kernel."""
 import os
 import shutil
