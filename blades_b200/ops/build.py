@@ -4,7 +4,7 @@
     blades_b200/_host.so   <- csrc/host/*.cpp  (g++ -O3)
 
 ``python -m blades_b200.ops.build [--force] [--verbose]``.  nvcc cross-compiles without a GPU.
-Objects are cached under ``build/`` keyed by source mtime; translation units compile in parallel.
+Objects are cached under ``build/`` keyed by content hash (stale ones are pruned after each link); translation units compile in parallel.
 """
 from __future__ import annotations
 
@@ -86,7 +86,16 @@ def build_cuda(force=False, verbose=False) -> str:
     _compile([nvcc, "-shared", "-o", CUDA_SO] + objs + ["-lcudart"], os.path.join(BUILD, "link_cuda.log"))
     with open(stamp_file, "w") as f:
         f.write(want)
+    _prune_objects(objs)
     return CUDA_SO
+
+
+def _prune_objects(current) -> None:
+    """Objects are keyed by content hash, so every source edit leaves an orphan behind: keep only the current set."""
+    keep = {os.path.basename(o) for o in current}
+    for f in os.listdir(BUILD):
+        if f.endswith((".o", ".o.log")) and f.replace(".log", "") not in keep:
+            os.remove(os.path.join(BUILD, f))
 
 
 def build_host(force=False, verbose=False) -> str:
