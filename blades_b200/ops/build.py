@@ -83,7 +83,9 @@ def build_cuda(force=False, verbose=False) -> str:
         for out in ex.map(lambda j: _compile(*j), jobs):
             if verbose:
                 print(out)
-    _compile([nvcc, "-shared", "-o", CUDA_SO] + objs + ["-lcudart"], os.path.join(BUILD, "link_cuda.log"))
+    # same -gencode at link time: otherwise nvcc adds an (empty) device-link stub for its default arch, sm_52
+    _compile([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", CUDA_SO] + objs + ["-lcudart"],
+             os.path.join(BUILD, "link_cuda.log"))
     with open(stamp_file, "w") as f:
         f.write(want)
     _prune_objects(objs)

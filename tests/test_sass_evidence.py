@@ -1,0 +1,90 @@
+"""Static checks on the built sm_100a library (no GPU needed): the hot kernels really use the Blackwell paths they
+claim (tcgen05 = UTC*MMA / UTCBAR / LDTM / UTCATOMSWS, TMA = UTMALDG, clusters = UCGABAR, mbarrier = SYNCS) and none
+of them spills to local memory."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "blades_b200", "_cuda.so")
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None or not os.path.exists(SO),
+                                reason="cuobjdump or the built library not available")
+
+
+@pytest.fixture(scope="module")
+def sass():
+    out = subprocess.run(["cuobjdump", "-sass", SO], capture_output=True, text=True).stdout
+    kernels, cur = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            kernels[cur] = []
+            continue
+        m = re.search(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", line)
+        if cur and m:
+            kernels[cur].append(m.group(1))
+    return kernels
+
+
+def _find(kernels, needle):
+    hits = [k for k in kernels if needle in k]
+    assert hits, f"no kernel matching {needle}"
+    return hits
+
+
+def _has(ops, prefix):
+    return any(o.startswith(prefix) for o in ops)
+
+
+def test_library_targets_sm_100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", SO], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+@pytest.mark.parametrize("kernel", ["gram_tcgen05_kernel", "wgrad_tcgen05_kernel"])
+def test_tensor_core_kernels_use_tcgen05_tmem_and_tma(sass, kernel):
+    for k in _find(sass, kernel):
+        ops = sass[k]
+        assert any(re.match(r"UTC\w*MMA", o) for o in ops), "no tcgen05.mma"
+        assert _has(ops, "UTCBAR"), "no tcgen05.commit"
+        assert _has(ops, "UTCATOMSWS"), "no TMEM allocation"
+        assert _has(ops, "LDTM"), "no tcgen05.ld"
+        assert _has(ops, "UTMALDG"), "no TMA load"
+        assert _has(ops, "SYNCS"), "no mbarrier"
+        assert not any(o.startswith("HMMA") or o.startswith("HGMMA") for o in ops), "legacy mma.sync / wgmma path"
+
+
+def test_implicit_gemm_wgrad_uses_4d_tma_boxes(sass):
+    ops = sass[_find(sass, "wgrad_tcgen05_kernel")[0]]
+    assert "UTMALDG.4D" in ops and "UTMALDG.2D" in ops
+
+
+def test_cluster_batchnorm_uses_cluster_barriers(sass):
+    for k in _find(sass, "client_bn_nhwc_fwd_cl_kernel") + _find(sass, "client_bn_nhwc_bwd_cl_kernel"):
+        assert _has(sass[k], "UCGABAR"), k
+
+
+def test_select_kernels_sort_in_registers_on_fmnmx(sass):
+    full = sass[_find(sass, "coord_select_kernelILi80ELi0E")[0]]
+    part = sass[_find(sass, "coord_select_part_kernelILi80E")[0]]
+    n_full, n_part = sum(o.startswith("FMNMX") for o in full), sum(o.startswith("FMNMX") for o in part)
+    assert n_full > 1600 and n_part < 0.85 * n_full, (n_full, n_part)
+    for ops in (full, part):
+        assert sum(o.startswith("LDG") for o in ops) >= 80           # one streaming load per client row
+
+
+def test_hot_kernels_do_not_spill():
+    res = subprocess.run(["cuobjdump", "-res-usage", SO], capture_output=True, text=True).stdout
+    usage = re.findall(r"Function (\S+):\n\s*REG:(\d+) STACK:(\d+) SHARED:\d+ LOCAL:(\d+)", res)
+    assert len(usage) > 40
+    hot = ("coord_select", "gram_tcgen05", "wgrad_tcgen05", "client_bn", "row_combine", "gather_samples", "attack")
+    for name, reg, stack, local in usage:
+        if any(h in name for h in hot):
+            assert int(stack) == 0 and int(local) == 0, (name, stack, local)
+            assert int(reg) <= 168, (name, reg)
