@@ -21,11 +21,19 @@ from typing import List, Sequence
 import torch
 import torch.distributed as dist
 
-__all__ = ["SymmetricUpdates", "round_up"]
+__all__ = ["SymmetricUpdates", "round_up", "coordinate_shards"]
 
 
 def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
+
+
+def coordinate_shards(d: int, world_size: int, align: int = 128):
+    """Coordinate ranges ``[(c_0, c_1), ...]`` owned by each rank for coordinate-sharded aggregation: contiguous,
+    disjoint, covering ``[0, d)``, interior boundaries aligned to ``align`` floats (512 B: whole 128 B row segments
+    per warp and TMA-box friendly).  Ranks at the end may own an empty range when ``d`` is tiny."""
+    cuts = [min(d, round_up(d * r // world_size, align)) for r in range(world_size)] + [d]
+    return [(cuts[r], cuts[r + 1]) for r in range(world_size)]
 
 
 class SymmetricUpdates:
@@ -54,10 +62,7 @@ class SymmetricUpdates:
         self.row_owner = []
         for r, k in enumerate(self.shard_sizes):
             self.row_owner += [(r, i) for i in range(k)]
-        # coordinate shards: boundaries aligned to 128 floats
-        G = world.size
-        cuts = [min(d, round_up(d * r // G, 128)) for r in range(G)] + [d]
-        self.col_ranges = [(cuts[r], cuts[r + 1]) for r in range(G)]
+        self.col_ranges = coordinate_shards(d, world.size)
 
     # ------------------------------------------------------------------ addressing
     def row_ptr(self, global_row: int) -> int:

@@ -66,3 +66,29 @@ def test_world_sizes_agree(agg, attack, local_steps, tmp_path):
                 assert torch.allclose(vec, results[world][0], atol=1e-6)
             else:
                 assert torch.allclose(vec, base, atol=1e-5), (world, r, (vec - base).abs().max())
+
+
+def test_coordinate_shard_emulation_single_process():
+    """Single-process emulation of the G coordinate shards (SURVEY 7.6 tests/dist): every rank reduces its own
+    coordinate range of ALL rows with the CPU oracle; concatenating the ranges reproduces the global aggregate."""
+    import torch
+    from blades_b200.comm.symm import coordinate_shards
+    from blades_b200.parallel.matrix import LocalMatrix
+    g = torch.Generator().manual_seed(0)
+    for d in (1, 127, 128, 129, 1000, 59850):
+        U = torch.randn(12, d, generator=g)
+        want_tm = LocalMatrix(U).trimmed_mean(3)
+        want_med = LocalMatrix(U).median()
+        w = torch.rand(12, generator=g)
+        want_comb = LocalMatrix(U).combine(w)
+        for G in (1, 2, 3, 4, 8):
+            shards = coordinate_shards(d, G)
+            assert shards[0][0] == 0 and shards[-1][1] == d
+            assert all(a1 == b0 for (_, a1), (b0, _) in zip(shards, shards[1:]))           # contiguous, disjoint
+            assert all(c0 % 128 == 0 for c0, _ in shards[1:] if c0 < d)                  # aligned interior cuts
+            parts_tm = [LocalMatrix(U[:, c0:c1]).trimmed_mean(3) for c0, c1 in shards if c1 > c0]
+            parts_med = [LocalMatrix(U[:, c0:c1]).median() for c0, c1 in shards if c1 > c0]
+            parts_comb = [LocalMatrix(U[:, c0:c1]).combine(w) for c0, c1 in shards if c1 > c0]
+            assert torch.equal(torch.cat(parts_tm), want_tm)
+            assert torch.equal(torch.cat(parts_med), want_med)
+            assert torch.allclose(torch.cat(parts_comb), want_comb)
