@@ -255,3 +255,20 @@ def test_toy_scene():
     assert res["mean"].norm() > 10          # dragged by outliers
     for k in ("krum", "geomed", "median", "autogm", "trimmed", "clippedclustering"):
         assert res[k].norm() < 10, (k, res[k])
+
+
+def test_autogm_textbook_mode_is_permutation_invariant_and_robust():
+    """Quirk Q6: the reference runs the water-filling in CLIENT order (its sort key is the index).  compat=False
+    sorts by distance, which makes the result independent of the order of the clients."""
+    from blades_b200.aggregators import Autogm
+    g = torch.Generator().manual_seed(4)
+    honest = torch.randn(14, 30, generator=g)
+    U = torch.cat([honest, honest.mean(0, keepdim=True) + 40.0 + torch.randn(6, 30, generator=g)])
+    perm = torch.randperm(len(U), generator=g)
+    a = Autogm(lamb=2.0, compat=False)(U)
+    b = Autogm(lamb=2.0, compat=False)(U[perm])
+    assert torch.allclose(a, b, atol=1e-5)
+    assert (a - honest.mean(0)).norm() < 0.2 * (U.mean(0) - honest.mean(0)).norm()
+    # the compat result is a valid robust aggregate too, but it depends on the client order for some inputs
+    c = Autogm(lamb=2.0, compat=True)(U)
+    assert (c - honest.mean(0)).norm() < 0.5 * (U.mean(0) - honest.mean(0)).norm()
