@@ -227,7 +227,8 @@ class RoundEngine:
         if not self.prefetch or not (on_cuda or self.prefetch_on_cpu):
             X, y = self._assemble(rows, num_batches, 0)
             self.h2d_bytes = X.numel() * X.element_size() + y.numel() * y.element_size()
-            return X.to(self.device, non_blocking=on_cuda), y.to(self.device, non_blocking=on_cuda)
+            # synchronous fallback: blocking copies, because the pinned staging buffer is reused by the next call
+            return X.to(self.device), y.to(self.device)
         key = (tuple(rows), num_batches)
         self.flush_prefetch()
         fut = self._pf_jobs.pop(key, None)
