@@ -126,6 +126,7 @@ class RoundEngine:
         self._pf_slot_of = {}       # request key -> next slot (0/1)
         self._pf_keyidx = {}        # request key -> index (names the pinned staging buffers)
         self._pf_pre = {}           # request key -> {client id: cursor before its unconsumed prefetched batch}
+        self._pf_copied = {}        # (request key, slot) -> event after the H2D copies out of its pinned staging
         self.track_cursors = False
         import os
         #: exercise the worker-thread prefetcher without a GPU (tests)
@@ -301,6 +302,9 @@ class RoundEngine:
         def job():
             if on_cuda:
                 torch.cuda.set_device(self.device)
+            prev = self._pf_copied.get((key, slot))
+            if prev is not None:
+                prev.synchronize()           # the H2D copy that last read this pinned staging buffer has finished
             self._snapshot_cursors(key, rows)
             X, y = self._assemble(rows, num_batches, staging)
             bufs = self._pf_dev.get((key, slot))
@@ -317,6 +321,7 @@ class RoundEngine:
                 bufs[1].copy_(y, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self._pf_stream)
+            self._pf_copied[(key, slot)] = ev
             return bufs[0], bufs[1], ev, slot
         return self._pf_pool.submit(job)
 
