@@ -135,7 +135,7 @@ def import_reference(num_devices: int = 1):
 
 
 # ------------------------------------------------------------------------------------------- headline workload
-def make_dataset(num_clients: int, batch: int, data_root: str, shape=(3, 32, 32), classes: int = 10):
+def make_dataset(num_clients: int, batch: int, data_root: str, shape=(3, 32, 32), classes: int = 10, train_sizes=None):
     import numpy as np
     from blades.datasets.basedataset import BaseDataset
 
@@ -148,7 +148,7 @@ def make_dataset(num_clients: int, batch: int, data_root: str, shape=(3, 32, 32)
             ids = list(range(num_clients))
             train, test = {}, {}
             for u in ids:
-                for store, n in ((train, 2 * batch), (test, batch)):
+                for store, n in ((train, train_sizes[u] if train_sizes else 2 * batch), (test, batch)):
                     y = rng.integers(0, classes, n)
                     x = (means[y] + rng.standard_normal((n,) + shape)).astype(np.float32)
                     store[u] = {"x": x, "y": y.astype(np.int64)}

@@ -14,7 +14,18 @@ from warnings import warn
 import numpy as np
 import torch
 
-__all__ = ["FLDataset"]
+__all__ = ["FLDataset", "RaggedBatches"]
+
+
+class RaggedBatches(Exception):
+    """Raised by ``FLDataset.get_train_batches`` when the requested batches cannot be stacked into one tensor
+    (a client reached the short tail batch of its shard, or shards of different sizes are out of phase).  The
+    batches have ALREADY been drawn from the streams; they travel with the exception so that nothing is lost:
+    ``batches[client_id] = [(X[b, ...] float32, y[b] int64), ...]`` (host tensors, transforms applied)."""
+
+    def __init__(self, batches):
+        super().__init__("batches of different sizes cannot be stacked; train them per size group")
+        self.batches = batches
 
 
 class FLDataset:
@@ -44,13 +55,15 @@ class FLDataset:
                           ) -> Tuple[torch.Tensor, torch.Tensor]:
         """Stack ``num_batches`` batches of each listed client:
         ``X[len(ids), k, B, ...]`` float32 and ``y[len(ids), k, B]`` int64, in reusable pinned memory.
-        All clients must yield equal batch shapes (true for the built-in generators
-        unless a client's shard is smaller than one batch)."""
+        All batches must have one shape; otherwise (the reference simply trains on the short tail batch of a
+        shard, basedataset.py:76-86) ``RaggedBatches`` is raised carrying the batches that were drawn."""
         fast = self._native_gather(client_ids, num_batches, pin, slot)
         if fast is not None:
             return fast
         rows = [self.get_train_data(c, num_batches) for c in client_ids]
         x0, y0 = rows[0][0]
+        if any(tuple(x.shape) != tuple(x0.shape) for batches in rows for x, _ in batches):
+            raise RaggedBatches({c: batches for c, batches in zip(client_ids, rows)})
         shape_x = (len(client_ids), num_batches) + tuple(x0.shape)
         shape_y = (len(client_ids), num_batches) + tuple(y0.shape)
         key = (shape_x, shape_y, slot)          # ``slot``: independent staging buffers for double buffering
@@ -63,8 +76,6 @@ class FLDataset:
         bx, by = buf
         for i, batches in enumerate(rows):
             for j, (x, y) in enumerate(batches):
-                if tuple(x.shape) != tuple(x0.shape):
-                    raise ValueError("ragged batch shapes; use the time-sliced engine")
                 bx[i, j].copy_(x)
                 by[i, j].copy_(y)
         return bx, by
@@ -88,13 +99,19 @@ class FLDataset:
         shp = streams[0].data.shape[1:]
         if not all(s.batch_size == bs and s.data.shape[1:] == shp for s in streams):
             return None
-        n, per = len(streams), num_batches * bs
+        n = len(streams)
+        drawn = [[s.next_indices() for _ in range(num_batches)] for s in streams]
+        lens = {len(sl) for per_client in drawn for sl in per_client}
+        if len(lens) != 1:
+            # short tail batches somewhere: hand the drawn batches to the caller (nothing is re-drawn or lost)
+            raise RaggedBatches({c: [(torch.from_numpy(np.ascontiguousarray(s.data[sl])).float(),
+                                      torch.from_numpy(np.ascontiguousarray(s.labels[sl])).long()) for sl in per_client]
+                                 for c, s, per_client in zip(client_ids, streams, drawn)})
+        bs = lens.pop()                       # every batch has this size (the shard's tail batch may be shorter)
+        per = num_batches * bs
         idx = np.empty((n, per), dtype=np.int64)
-        for i, s in enumerate(streams):
-            for j in range(num_batches):
-                sl = s.next_indices()
-                if len(sl) != bs:
-                    return self._ragged_restart()
+        for i, per_client in enumerate(drawn):
+            for j, sl in enumerate(per_client):
                 idx[i, j * bs:(j + 1) * bs] = sl
         shape_x = (n, num_batches, bs) + tuple(shp)
         shape_y = (n, num_batches, bs)
@@ -135,9 +152,6 @@ class FLDataset:
                 s.data, s.labels = px.numpy(), py.numpy()
                 s._pinned = True
         return streams, tuple(shp), bs
-
-    def _ragged_restart(self):
-        raise ValueError("ragged batch (client shard not a multiple of the batch size); use get_train_data")
 
     def state_dict(self) -> dict:
         """Data cursors for checkpoint/resume (generators that expose ``state()``)."""

@@ -30,6 +30,7 @@ import torch.nn as nn
 
 from ..client import BladesClient, ByzantineClient
 from ..comm.group import World, split_clients
+from ..datasets.dataset import RaggedBatches
 from ..parallel.matrix import LocalMatrix, UpdateMatrix, VirtualRows
 from ..server import BladesServer
 from . import batched as cb
@@ -127,6 +128,8 @@ class RoundEngine:
         self._pf_keyidx = {}        # request key -> index (names the pinned staging buffers)
         self._pf_pre = {}           # request key -> {client id: cursor before its unconsumed prefetched batch}
         self._pf_copied = {}        # (request key, slot) -> event after the H2D copies out of its pinned staging
+        self._stash = {}            # request key -> inputs (or RaggedBatches) handed back by a caller that could not use them
+        self._ragged_data = {}      # local row -> pre-drawn host batches for the time-sliced path
         self.track_cursors = False
         import os
         #: exercise the worker-thread prefetcher without a GPU (tests)
@@ -225,6 +228,11 @@ class RoundEngine:
         chunk has not consumed yet."""
         rows = list(range(len(self.local_idx))) if rows is None else list(rows)
         on_cuda = self.device.type == "cuda"
+        back = self._stash.pop((tuple(rows), num_batches), None)
+        if back is not None:                 # inputs staged earlier for a path that had to decline them
+            if isinstance(back, RaggedBatches):
+                raise back
+            return back
         if not self.prefetch or not (on_cuda or self.prefetch_on_cpu):
             X, y = self._assemble(rows, num_batches, 0)
             self.h2d_bytes = X.numel() * X.element_size() + y.numel() * y.element_size()
@@ -235,9 +243,18 @@ class RoundEngine:
         fut = self._pf_jobs.pop(key, None)
         if fut is None:
             fut = self._pf_submit(rows, num_batches)
-        X, y, ev, slot = fut.result()
-        self._pf_pre.pop(key, None)                      # that batch is consumed now
         consumed = None
+        try:
+            X, y, ev, slot = fut.result()
+        except RaggedBatches:
+            # the batches of this round cannot be stacked (they travel with the exception); keep prefetching
+            self._pf_pre.pop(key, None)
+            if on_cuda:
+                consumed = torch.cuda.Event()
+                consumed.record(torch.cuda.current_stream(self.device))
+            self._pf_deferred = (key, rows, num_batches, consumed)
+            raise
+        self._pf_pre.pop(key, None)                      # that batch is consumed now
         if on_cuda:
             torch.cuda.current_stream(self.device).wait_event(ev)
         self.h2d_bytes = X.numel() * X.element_size() + y.numel() * y.element_size()
@@ -418,7 +435,11 @@ class RoundEngine:
             if X.shape[0] != len(rows):
                 X, y = X[rows[0]: rows[-1] + 1], y[rows[0]: rows[-1] + 1]
         else:
-            X, y = self.stage_batches(rows, 1)
+            try:
+                X, y = self.stage_batches(rows, 1)
+            except RaggedBatches as e:
+                self._train_ragged(rows, lr, e.batches)
+                return
         if not self._graph_eligible(rows):
             self.last_client_losses = self._batched_step(rows, lr, X.clone(), y.clone())
             return
@@ -453,6 +474,24 @@ class RoundEngine:
         _loader.count_launch(n_native)               # our kernels inside the replayed graph
         self.last_client_losses = losses
 
+    def _train_ragged(self, rows: List[int], lr: float, batches) -> None:
+        """fedsgd round whose batches have different sizes (tail batches of shards that are not a multiple of the
+        batch size, out of phase across clients): one eager fused pass per size group.  The reference just trains
+        each client on whatever its generator yields (client.py:178-193)."""
+        groups = {}
+        for r in rows:
+            x, _ = batches[self.clients[self.local_idx[r]].id()][0]
+            groups.setdefault(tuple(x.shape), []).append(r)
+        losses = torch.zeros(len(rows), device=self.device)
+        pos = {r: i for i, r in enumerate(rows)}
+        for _, grp in sorted(groups.items(), key=lambda kv: kv[1][0]):
+            xs = torch.stack([batches[self.clients[self.local_idx[r]].id()][0][0] for r in grp])
+            ys = torch.stack([batches[self.clients[self.local_idx[r]].id()][0][1] for r in grp])
+            X = xs.unsqueeze(1).to(self.device, torch.float32)
+            y = ys.unsqueeze(1).to(self.device)
+            losses[[pos[r] for r in grp]] = self._batched_step(grp, lr, X, y).to(losses.dtype)
+        self.last_client_losses = losses
+
     # -- whole-round CUDA graph ------------------------------------------------------------
     def all_rows_static(self) -> bool:
         import os
@@ -484,7 +523,14 @@ class RoundEngine:
         if self.prestaged is not None:
             X, y = self.prestaged
         else:
-            X, y = self.stage_batches(rows, 1)
+            try:
+                X, y = self.stage_batches(rows, 1)
+            except RaggedBatches as e:
+                self._stash[(tuple(rows), 1)] = e        # the eager round picks these batches up again
+                return False
+        if "graph" in st and tuple(X.shape) != tuple(st["sx"].shape):
+            self._stash[(tuple(rows), 1)] = (X, y)       # e.g. the shorter tail batch of an epoch: not this graph
+            return False
         if "graph" not in st:
             sx, sy = X.clone(), y.clone()
             self._clamp_tensor(rows)
@@ -648,7 +694,13 @@ class RoundEngine:
             prev = self._slice_copied.get(wi)
             if prev is not None:
                 prev.synchronize()                     # the pinned slot of this worker is free again
-            X, y = self.dataset.get_train_batches([c.id()], local_steps, slot=100 + wi)   # pinned [1,k,B,..]
+            try:
+                X, y = self.dataset.get_train_batches([c.id()], local_steps, slot=100 + wi)   # pinned [1,k,B,..]
+            except RaggedBatches as e:
+                # this visit contains a short tail batch: it runs on the eager time-sliced path with these batches
+                self._ragged_data[r] = e.batches[c.id()]
+                rest.append(r)
+                continue
             X, y = X[0], y[0]
             key = (wi,) + self._sliced_graph_key(c, local_steps, lr, X.shape)
             st = self._sliced_graphs.get(key)
@@ -678,7 +730,7 @@ class RoundEngine:
             c._state["saved_update"] = self.U[r]
         for _, _, stream in workers:
             main.wait_stream(stream)
-        return rest
+        return sorted(rest)
 
     def _train_timesliced(self, r: int, local_steps: int, lr: float) -> None:
         gi = self.local_idx[r]
@@ -694,7 +746,9 @@ class RoundEngine:
             c.on_train_round_begin()
         else:
             self.worker.train()
-        data = self.dataset.get_train_data(c.id(), local_steps)
+        data = self._ragged_data.pop(r, None)           # batches already drawn by a path that could not stack them
+        if data is None:
+            data = self.dataset.get_train_data(c.id(), local_steps)
         c.local_training(data_batches=data)
         if custom_end:
             c.on_train_round_end()          # client computes/saves its own update (lands in U via bind_row)

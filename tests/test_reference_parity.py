@@ -121,14 +121,14 @@ def test_alie_zmax_matches_reference(ref, n, f):
     assert abs(float(got) - float(want)) < 1e-6
 
 
-def _run_both(tmp, attack, attack_kws, agg, agg_kws, rounds, local_steps, n=6, f=2, bs=8, seed=3):
+def _run_both(tmp, attack, attack_kws, agg, agg_kws, rounds, local_steps, n=6, f=2, bs=8, seed=3, train_sizes=None):
     """Same data (the reference's cache file is read back by our BaseDataset), same seed, same API calls:
     returns (reference parameters, our parameters) after ``rounds`` rounds."""
     import pickle
     from baseline import ref_arm
     rs = ref_arm.import_reference(0)
     from blades.models.mnist import MLP as RefMLP
-    ds_ref = ref_arm.make_dataset(n, bs, os.path.join(tmp, "ref"), shape=(28, 28))
+    ds_ref = ref_arm.make_dataset(n, bs, os.path.join(tmp, "ref"), shape=(28, 28), train_sizes=train_sizes)
     kw = dict(num_byzantine=f if attack else 0, attack=attack, attack_kws=attack_kws, aggregator=agg,
               aggregator_kws=agg_kws, use_cuda=False, seed=seed)
     run_kw = dict(global_rounds=rounds, local_steps=local_steps, validate_interval=1000, server_lr=1.0, client_lr=0.1)
@@ -537,3 +537,28 @@ def test_torch_utils_match_reference(ref):
     assert abs(float(rtu.l2norm(s1)) - float(otu.l2norm(s1))) < 1e-6
     x = torch.randn(4, 7, generator=g)
     assert torch.allclose(rtu.HLoss()(x), otu.HLoss()(x))
+
+
+@pytest.mark.parametrize("sizes,local_steps,rounds", [
+    ([20] * 6, 1, 7),                       # every shard ends in a short batch of 4 (8, 8, 4): uniform tails
+    ([20, 24, 28, 17, 16, 31], 1, 9),       # tails of different sizes, out of phase across clients
+    ([20, 24, 28, 17, 16, 31], 3, 4),       # fedavg visits that contain a short batch
+])
+def test_short_tail_batches_match_reference(ref, tmp_path, sizes, local_steps, rounds):
+    """Shards that are not a multiple of the batch size: the reference trains on the short tail batch; so must the
+    client-batched engine (per-size groups) -- compared end to end across several epochs."""
+    want, got = _run_both(str(tmp_path), "ipm", {"epsilon": 0.5}, "median", None, rounds, local_steps, train_sizes=sizes)
+    err = (got - want).abs().max().item()
+    assert torch.isfinite(want).all() and err <= 1e-5 * max(1.0, want.abs().max().item()), err
+
+
+@pytest.mark.parametrize("chunk", ["0", "2"])
+def test_short_tail_batches_with_prefetcher_match_reference(ref, tmp_path, monkeypatch, chunk):
+    """Same as above with the one-round-ahead prefetcher (the ragged batches travel through the worker thread's
+    future) and chunked requests."""
+    monkeypatch.setenv("BLADES_PREFETCH_CPU", "1")
+    monkeypatch.setenv("BLADES_MAX_BATCHED_CLIENTS", chunk)
+    want, got = _run_both(str(tmp_path), "alie", {"num_clients": 6, "num_byzantine": 2}, "trimmedmean", {"nb": 2}, 9, 1,
+                          train_sizes=[20, 24, 28, 17, 16, 31])
+    err = (got - want).abs().max().item()
+    assert err <= 1e-5 * max(1.0, want.abs().max().item()), err
