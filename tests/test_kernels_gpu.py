@@ -599,4 +599,4 @@ def test_short_tail_batches_on_gpu(monkeypatch, tmp_path, local_steps):
         return sim.engine.gflat.theta.clone()
     a, b = run("1"), run("0")
     assert torch.isfinite(a).all()
-    assert torch.allclose(a, b, atol=2e-3, rtol=2e-2), (a - b).abs().max()
+    assert torch.allclose(a, b, atol=5e-3, rtol=5e-2), (a - b).abs().max()   # tf32 wgrad (graphed) vs fp32 autograd (eager fedavg)
