@@ -143,6 +143,8 @@ class RoundEngine:
         self._round_graphs = {}     # (client lr, server lr) -> captured whole-round graph state
         self.static_aggregate = None
         self._graphs = {}           # (rows, lr, shape) -> (CUDAGraph, static X, static y, losses)
+        self._graph_seen = {}       # graph key -> how often it was requested (capture on the second request)
+        self._graph_lr = {}         # captured graph key -> learning rate baked into it
         self.prestaged = None       # optional (X[n,1,B,...], y[n,1,B]) already on the device
         self.h2d_bytes = 0
 
@@ -445,6 +447,10 @@ class RoundEngine:
             return
         key = (tuple(rows), float(lr), tuple(X.shape))
         entry = self._graphs.get(key)
+        if entry is None and not self._worth_capturing(self._graphs, key, lr):
+            # first round with this (rows, lr, shape): run eagerly; a graph is captured when it comes back
+            self.last_client_losses = self._batched_step(rows, lr, X.clone(), y.clone())
+            return
         if entry is None:
             self._clamp_tensor(rows)
             sx, sy = X.clone(), y.clone()        # static input buffers owned by the graph
@@ -473,6 +479,27 @@ class RoundEngine:
         from ..ops import _loader
         _loader.count_launch(n_native)               # our kernels inside the replayed graph
         self.last_client_losses = losses
+
+    def _worth_capturing(self, cache: dict, key, lr: float) -> bool:
+        """Capture policy shared by the step graphs and the fedavg visit graphs.  The learning rate is baked into a
+        captured graph (it is the epilogue scale of the wgrad / BatchNorm kernels), so a schedule that changes it
+        every round would otherwise capture -- and keep -- a new graph per round.  A key is captured the SECOND time
+        it is requested; graphs of at most two distinct learning rates are kept (piecewise-constant schedules such
+        as the reference's MultiStepLR replay graphs almost always; continuously varying ones simply run eagerly)."""
+        seen = self._graph_seen[key] = self._graph_seen.get(key, 0) + 1
+        if len(self._graph_seen) > 512:
+            self._graph_seen = {key: seen}
+        if seen < 2:
+            return False
+        lrs = []
+        for k in cache:
+            if self._graph_lr[k] not in lrs:
+                lrs.append(self._graph_lr[k])
+        if float(lr) not in lrs and len(lrs) >= 2:
+            for k in [k for k in cache if self._graph_lr[k] == lrs[0]]:
+                del cache[k], self._graph_lr[k]
+        self._graph_lr[key] = float(lr)
+        return True
 
     def _train_ragged(self, rows: List[int], lr: float, batches) -> None:
         """fedsgd round whose batches have different sizes (tail batches of shards that are not a multiple of the
@@ -704,6 +731,10 @@ class RoundEngine:
             X, y = X[0], y[0]
             key = (wi,) + self._sliced_graph_key(c, local_steps, lr, X.shape)
             st = self._sliced_graphs.get(key)
+            if st is None and not self._worth_capturing(self._sliced_graphs, key, lr):
+                self._ragged_data[r] = [(X[j].clone(), y[j].clone()) for j in range(local_steps)]   # eager this time
+                rest.append(r)
+                continue
             with torch.cuda.stream(stream):
                 stream.wait_event(ready)
                 if st is None:

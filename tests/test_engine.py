@@ -340,3 +340,33 @@ def test_checkpoint_resume_is_exact_with_prefetch_and_chunking(tmp_path, monkeyp
     mb = MLP()
     make("c").run(mb, global_rounds=6, resume=ck, **kw)
     assert torch.allclose(torch.cat([p.detach().reshape(-1) for p in mb.parameters()]), final, atol=1e-7)
+
+
+def test_graph_capture_policy_bounds_the_cache():
+    """Learning rates are baked into captured graphs: capture on the second request of a key, keep graphs of at most
+    two distinct learning rates (pure host logic of RoundEngine._worth_capturing)."""
+    from blades_b200.engine.round import RoundEngine
+    eng = RoundEngine.__new__(RoundEngine)
+    eng._graph_seen, eng._graph_lr = {}, {}
+    cache = {}
+
+    def request(lr, rows=(0, 1)):
+        key = (rows, float(lr), (2, 1, 8, 28, 28))
+        if key in cache:
+            return "replay"
+        if eng._worth_capturing(cache, key, lr):
+            cache[key] = object()
+            return "capture"
+        return "eager"
+    assert [request(0.1) for _ in range(4)] == ["eager", "capture", "replay", "replay"]
+    assert [request(0.01) for _ in range(3)] == ["eager", "capture", "replay"]                 # MultiStepLR drop
+    assert request(0.1) == "replay" and len(cache) == 2
+    assert [request(0.001) for _ in range(2)] == ["eager", "capture"]                          # third lr: oldest evicted
+    assert {k[1] for k in cache} == {0.01, 0.001}
+    # a schedule that changes the lr every round never captures anything
+    before = len(cache)
+    assert all(request(0.1 * 0.99 ** i) == "eager" for i in range(1, 40))
+    assert len(cache) == before
+    # chunked rounds: several keys share one lr and are all kept
+    assert [request(0.001, rows=(2, 3)) for _ in range(2)] == ["eager", "capture"]
+    assert len({k[1] for k in cache}) == 2
