@@ -8,5 +8,6 @@ setup(
     package_data={"blades_b200": ["*.so", "csrc/cuda/*", "csrc/cuda/gen/*", "csrc/host/*", "csrc/*.py"]},
     python_requires=">=3.9",
     install_requires=["torch", "numpy"],
+    extras_require={"data": ["torchvision"], "test": ["pytest", "hypothesis", "scikit-learn", "scipy", "pandas"]},
     zip_safe=False,
 )
