@@ -179,7 +179,7 @@ class RoundEngine:
         return self.server
 
     def _alloc_updates(self, n_local: int, d: int) -> None:
-        if self.world.distributed and self.device.type == "cuda":
+        if self.world.distributed and self.device.type == "cuda" and self._peer_access_everywhere():
             from ..comm import symm
             self.symm = symm.SymmetricUpdates(self.world, self.shard_sizes, d)
             self.U = self.symm.local
@@ -187,6 +187,19 @@ class RoundEngine:
             self.symm = None
             ld = (d + 63) // 64 * 64          # 256 B aligned rows: 16 B vector loads + TMA strides
             self.U = torch.zeros(max(n_local, 1), ld, device=self.device, dtype=torch.float32)[:n_local, :d]
+
+    def _peer_access_everywhere(self) -> bool:
+        """``BLADES_SYMM=0`` (set identically on every rank) disables the NVLink symmetric-memory path: rows are then
+        gathered with NCCL and every rank aggregates the dense matrix itself -- the slower baseline path, also what
+        the CPU/gloo runs use.  By default symmetric memory is required on a multi-GPU run and a failing rendezvous
+        (no peer access) raises."""
+        import os
+        if os.environ.get("BLADES_SYMM", "1") != "0":
+            return True
+        if self.world.rank == 0:
+            import logging
+            logging.getLogger("debug").warning("BLADES_SYMM=0: NCCL all_gather + per-rank aggregation")
+        return False
 
     # ------------------------------------------------------------------ training
     def _stock_for_batching(self, c: BladesClient) -> bool:
