@@ -562,3 +562,27 @@ def test_short_tail_batches_with_prefetcher_match_reference(ref, tmp_path, monke
                           train_sizes=[20, 24, 28, 17, 16, 31])
     err = (got - want).abs().max().item()
     assert err <= 1e-5 * max(1.0, want.abs().max().item()), err
+
+
+def test_fuzzed_simulations_match_reference(ref, tmp_path):
+    """Ten random (attack, aggregator, #clients, shard sizes not multiples of the batch size, fedsgd / fedavg, rounds)
+    simulations through both public APIs end at the same global model."""
+    import random as _random
+    rng = _random.Random(2024)                    # own generator: the simulators reseed the global one
+    attacks = [(None, None), ("ipm", {"epsilon": 0.5}), ("ipm", {"epsilon": 5.0}), ("alie", "auto"),
+               ("noise", {"mean": 0.0, "std": 0.5}), ("labelflipping", None), ("signflipping", None)]
+    aggs = [("mean", None), ("median", None), ("trimmedmean", "nb"), ("krum", "nf"), ("geomed", None),
+            ("autogm", {"lamb": 2.0}), ("centeredclipping", {"tau": 5.0, "n_iter": 3})]
+    for it in range(10):
+        n, f = rng.choice([6, 8, 9]), rng.choice([1, 2])
+        atk, akw = rng.choice(attacks)
+        akw = {"num_clients": n, "num_byzantine": f} if akw == "auto" else akw
+        agg, gkw = rng.choice(aggs)
+        gkw = {"nb": f} if gkw == "nb" else ({"num_clients": n, "num_byzantine": f} if gkw == "nf" else gkw)
+        bs = rng.choice([4, 8])
+        sizes = [rng.choice([bs * 2, bs * 2 + 3, bs * 3 - 1, bs * 4]) for _ in range(n)]
+        ls, rounds = rng.choice([1, 1, 2, 3]), rng.choice([3, 5])
+        want, got = _run_both(str(tmp_path / str(it)), atk, akw, agg, gkw, rounds, ls, n=n, f=f, bs=bs,
+                              train_sizes=sizes, seed=rng.randint(0, 99))
+        err = (got - want).abs().max().item()
+        assert err <= 1e-5 * max(1.0, want.abs().max().item()), (it, atk, agg, sizes, ls, rounds, err)
