@@ -586,3 +586,62 @@ def test_fuzzed_simulations_match_reference(ref, tmp_path):
                               train_sizes=sizes, seed=rng.randint(0, 99))
         err = (got - want).abs().max().item()
         assert err <= 1e-5 * max(1.0, want.abs().max().item()), (it, atk, agg, sizes, ls, rounds, err)
+
+
+def _run_both_models(tmp, make_ref_model, make_our_model, rounds, local_steps, n, bs, seed=4, lr=0.05):
+    """CIFAR-shaped variant of ``_run_both`` with arbitrary models (IPM + median, one Byzantine client)."""
+    import pickle
+    from baseline import ref_arm
+    rs = ref_arm.import_reference(0)
+    ds_ref = ref_arm.make_dataset(n, bs, os.path.join(tmp, "ref"), shape=(3, 32, 32))
+    kw = dict(num_byzantine=1, attack="ipm", attack_kws={"epsilon": 0.5}, aggregator="median", seed=seed)
+    run_kw = dict(global_rounds=rounds, local_steps=local_steps, validate_interval=1000, server_lr=1.0, client_lr=lr)
+    # parameters that are not owned by a module with ``reset_parameters`` (CCT's positional embedding) keep their
+    # constructor initialisation through ``reset_model_weights``: build both models from the same RNG state
+    torch.manual_seed(1234)
+    m_ref = make_ref_model()
+    rs.Simulator(dataset=ds_ref, num_actors=1, log_path=os.path.join(tmp, "lr"), **kw).run(m_ref, **run_kw)
+    from blades_b200 import Simulator
+    from blades_b200.datasets import BaseDataset
+
+    class Same(BaseDataset):
+        compat = True
+
+        def generate_datasets(self, path="./data", iid=True, alpha=0.1, num_clients=20, seed=1):
+            with open(os.path.join(tmp, "ref", "SyntheticCIFAR10.obj"), "rb") as fh:
+                _, a, b, c, d = [pickle.load(fh) for _ in range(5)]
+            return a, b, c, d
+
+    torch.manual_seed(1234)
+    m = make_our_model()        # same order as on the reference side: model first, then Simulator (which seeds), then run
+    sim = Simulator(dataset=Same(data_root=os.path.join(tmp, "ours"), train_bs=bs, num_clients=n, seed=1),
+                    log_path=os.path.join(tmp, "lo"), progress=False, **kw)
+    sim.run(m, **run_kw)
+    assert sim.engine.batchable_model           # the client-batched engine (not the time-sliced oracle) ran fedsgd
+    ra, oa = dict(m_ref.named_parameters()), dict(m.named_parameters())
+    assert list(ra) == list(oa)
+    return max((ra[k].detach() - oa[k].detach()).abs().max().item() for k in ra)
+
+
+@pytest.mark.parametrize("local_steps", [1, 2])
+def test_cct_simulation_matches_reference(ref, tmp_path, local_steps):
+    """Conv tokenizer + transformer encoder (LayerNorm, attention, seq-pool, positional embedding) through the
+    client-batched engine == the reference's per-client training (dropout / stochastic depth off: the reference draws
+    one mask per client, the fused pass one mask for all)."""
+    import blades_b200.models.cifar10.cctnets as oc
+    rc = ref.import_module("blades.models.cifar10.cctnets.cct")
+    kw = dict(attention_dropout=0.0, stochastic_depth=0.0, dropout=0.0)
+    err = _run_both_models(str(tmp_path), lambda: rc.cct_2_3x2_32(**kw), lambda: oc.cct_2_3x2_32(**kw), 2, local_steps,
+                           n=4, bs=4)
+    assert err < 5e-6, err
+
+
+def test_resnet18_round_matches_reference(ref, tmp_path):
+    """One fedsgd round of ResNet-18 (torchvision's model on the reference side): convolutions, per-client BatchNorm,
+    max-pool, residual adds through the client-batched engine.  One round only: with BatchNorm over 16 values per
+    channel at 1x1 resolution a 1e-7 weight perturbation already changes the next gradient by 4e-2 (plain PyTorch)."""
+    import torchvision
+    from blades_b200.models import resnet18
+    err = _run_both_models(str(tmp_path), lambda: torchvision.models.resnet18(num_classes=10), lambda: resnet18(10), 1, 1,
+                           n=2, bs=16)
+    assert err < 5e-6, err
