@@ -85,7 +85,8 @@ class BatchStream:
     # -- checkpointing -------------------------------------------------------------
     def state(self) -> dict:
         return {"rng": self._rng.bit_generator.state, "epoch": self._epoch, "pos": self._pos,
-                "perm": None if self._perm is None else self._perm.copy(), "started": self._started}
+                # ``_perm`` is replaced, never mutated in place: a reference is a consistent O(1) snapshot
+                "perm": self._perm, "started": self._started}
 
     def load_state(self, st: dict) -> None:
         self._rng.bit_generator.state = st["rng"]

@@ -304,7 +304,7 @@ class RoundEngine:
     def _snapshot_cursors(self, key, rows) -> None:
         """Per-client stream cursors right BEFORE the batches of a prefetch are drawn: what a checkpoint must
         store for these clients while that prefetched batch is still unconsumed (``data_cursors``)."""
-        if self.track_cursors and hasattr(self.dataset, "stream_state"):
+        if hasattr(self.dataset, "stream_state"):
             self._pf_pre[key] = {self.clients[self.local_idx[r]].id():
                                  self.dataset.stream_state(self.clients[self.local_idx[r]].id()) for r in rows}
 
@@ -417,6 +417,26 @@ class RoundEngine:
             def result(self):
                 return self.v
         return _Done((plan["X"][slot], plan["y"][slot], ev, slot))
+
+    def finish(self) -> None:
+        """End of a run: give back the batches the prefetcher drew for a round that will not happen (the streams are
+        rewound to the cursors snapshotted before those draws), so a following ``run`` / evaluation / checkpoint sees
+        the data streams exactly where the last trained round left them; stop the worker thread."""
+        self._pf_deferred = None
+        for fut in list(self._pf_jobs.values()):
+            try:
+                fut.result()
+            except RaggedBatches:
+                pass
+        self._pf_jobs.clear()
+        if hasattr(self.dataset, "load_state_dict"):
+            for pre in self._pf_pre.values():
+                self.dataset.load_state_dict(pre)
+        self._pf_pre.clear()
+        self._stash.clear()
+        if self._pf_pool is not None:
+            self._pf_pool.shutdown(wait=True)
+            self._pf_pool = None
 
     def data_cursors(self):
         """Data-stream cursors as of the batches CONSUMED so far.  The prefetcher runs one round ahead: for every

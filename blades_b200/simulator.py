@@ -541,6 +541,7 @@ class Simulator(object):
                     self.client_lr = client_lr
                     save_checkpoint(checkpoint_path, self, server_lr_scheduler, client_lr_scheduler)
         self.client_lr = client_lr
+        self.engine.finish()          # rewind batches prefetched for a round that will not happen
         return ret
 
     def __str__(self):

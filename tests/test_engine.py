@@ -370,3 +370,23 @@ def test_graph_capture_policy_bounds_the_cache():
     # chunked rounds: several keys share one lr and are all kept
     assert [request(0.001, rows=(2, 3)) for _ in range(2)] == ["eager", "capture"]
     assert len({k[1] for k in cache}) == 2
+
+
+def test_consecutive_runs_continue_the_data_streams(tmp_path, monkeypatch):
+    """run(3 rounds) then run(3 rounds) on one Simulator consumes the same batches as it would without the
+    one-round-ahead prefetcher: the batch prefetched for the round after the last one is given back."""
+    def go(prefetch):
+        monkeypatch.setenv("BLADES_PREFETCH_CPU", prefetch)
+        ds = synthetic_fldataset(4, shape=(28, 28), num_classes=10, train_bs=8, train_per_client=40, test_per_client=8, seed=6)
+        sim = Simulator(ds, aggregator="mean", log_path=str(tmp_path / f"p{prefetch}"), seed=1, progress=False)
+        outs = []
+        for _ in range(2):
+            torch.manual_seed(0)
+            m = MLP()
+            sim.run(m, global_rounds=3, local_steps=1, server_lr=1.0, client_lr=0.1, validate_interval=100)
+            outs.append(torch.cat([p.detach().reshape(-1) for p in m.parameters()]))
+        return outs, sim.dataset.state_dict()
+    (a1, a2), sa = go("1")
+    (b1, b2), sb = go("0")
+    assert torch.equal(a1, b1) and torch.equal(a2, b2)
+    assert all(sa[k]["pos"] == sb[k]["pos"] and sa[k]["epoch"] == sb[k]["epoch"] for k in sa)
