@@ -627,6 +627,8 @@ class RoundEngine:
         """Per-client loss clamps as a device tensor (cached: no H2D copy inside a graph capture)."""
         key = tuple(rows)
         t = self._clamps.get(key)
+        if t is None and len(self._clamps) > 256:        # ragged rounds request ever-changing row groups
+            self._clamps.clear()
         if t is None:
             t = self._clamps[key] = torch.tensor(
                 [float(self.clients[self.local_idx[r]].loss_clamp) for r in rows], device=self.device)
