@@ -119,6 +119,7 @@ class RoundEngine:
         self.last_client_losses: Optional[torch.Tensor] = None
         self.kernel_launches = 0
         self._clamps = {}
+        self._clamps_in_graphs = set()
         self._pf_pool = None
         self._pf_stream = None
         self._zc_plans = {}
@@ -486,6 +487,7 @@ class RoundEngine:
             return
         if entry is None:
             self._clamp_tensor(rows)
+            self._clamps_in_graphs.add(tuple(rows))
             sx, sy = X.clone(), y.clone()        # static input buffers owned by the graph
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
@@ -594,6 +596,7 @@ class RoundEngine:
         if "graph" not in st:
             sx, sy = X.clone(), y.clone()
             self._clamp_tensor(rows)
+            self._clamps_in_graphs.add(tuple(rows))
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
             before = _loader.LAUNCHES
@@ -628,7 +631,8 @@ class RoundEngine:
         key = tuple(rows)
         t = self._clamps.get(key)
         if t is None and len(self._clamps) > 256:        # ragged rounds request ever-changing row groups
-            self._clamps.clear()
+            # captured graphs have the address of their clamp tensor baked in: those entries must stay alive
+            self._clamps = {k: v for k, v in self._clamps.items() if k in self._clamps_in_graphs}
         if t is None:
             t = self._clamps[key] = torch.tensor(
                 [float(self.clients[self.local_idx[r]].loss_clamp) for r in rows], device=self.device)
