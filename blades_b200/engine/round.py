@@ -36,6 +36,11 @@ from ..server import BladesServer
 from . import batched as cb
 from .flat import FlatParams
 
+#: stream-capture mode of every CUDA graph the engine records.  "thread_local": only the capturing thread is policed --
+#: the input prefetcher's worker thread may allocate / copy / synchronise on its own stream while a chunk's graph is
+#: being captured (the default "global" mode would fail the capture for that).
+_CAPTURE_MODE = "thread_local"
+
 __all__ = ["RoundEngine", "PhaseTimer"]
 
 
@@ -502,7 +507,7 @@ class RoundEngine:
             sy.copy_(y)
             from ..ops import _loader
             before = _loader.LAUNCHES
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode=_CAPTURE_MODE):
                 losses = self._batched_step(rows, lr, sx, sy)
             entry = self._graphs[key] = (graph, sx, sy, losses, _loader.LAUNCHES - before)
             _loader.count_launch(-entry[4])          # capture does not execute
@@ -601,7 +606,7 @@ class RoundEngine:
             graph = torch.cuda.CUDAGraph()
             before = _loader.LAUNCHES
             try:
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph, capture_error_mode=_CAPTURE_MODE):
                     losses = self._batched_step(rows, lr, sx, sy)
                     agg = aggregate_fn()
                 mat = matrix_fn()
@@ -786,7 +791,7 @@ class RoundEngine:
                         self._sliced_body(c, local_steps, lr, sx, sy, scratch, (model_w, flat_w))
                     stream.synchronize()
                     graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph, stream=stream):
+                    with torch.cuda.graph(graph, stream=stream, capture_error_mode=_CAPTURE_MODE):
                         loss = self._sliced_body(c, local_steps, lr, sx, sy, scratch, (model_w, flat_w))
                     st = self._sliced_graphs[key] = (graph, sx, sy, scratch, loss)
                 graph, sx, sy, scratch, loss = st
