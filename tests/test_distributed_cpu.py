@@ -92,3 +92,41 @@ def test_coordinate_shard_emulation_single_process():
             assert torch.equal(torch.cat(parts_tm), want_tm)
             assert torch.equal(torch.cat(parts_med), want_med)
             assert torch.allclose(torch.cat(parts_comb), want_comb)
+
+
+def _run_ckpt(rank, world, port, out_dir, phase):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    torch.set_num_threads(1)
+    from blades_b200 import Simulator
+    from blades_b200.comm.group import init_world, shutdown
+    from blades_b200.datasets import synthetic_fldataset
+    from blades_b200.models import MLP
+    init_world(use_cuda=False)
+    ds = synthetic_fldataset(6, shape=(28, 28), train_bs=8, train_per_client=20, test_per_client=8, seed=3)   # 8, 8, 4
+    sim = Simulator(ds, num_byzantine=2, attack="noise", aggregator="centeredclipping",
+                    log_path=os.path.join(out_dir, "logs" + phase), seed=1, progress=False)
+    torch.manual_seed(5)
+    m = MLP()
+    ck = os.path.join(out_dir, "ck.pt")
+    kw = dict(local_steps=1, server_lr=1.0, client_lr=0.1, validate_interval=100)
+    if phase == "full":
+        sim.run(m, global_rounds=7, **kw)
+    elif phase == "first":
+        sim.run(m, global_rounds=4, checkpoint_path=ck, checkpoint_interval=4, **kw)
+    else:
+        sim.run(m, global_rounds=7, resume=ck, **kw)
+    torch.save(torch.cat([p.detach().reshape(-1) for p in m.parameters()]), os.path.join(out_dir, f"{phase}_{rank}.pt"))
+    shutdown()
+
+
+def test_distributed_checkpoint_resume_is_exact(tmp_path):
+    """Two ranks: each rank owns different clients (their stream cursors) and its own RNG stream (the noise attacker
+    lives on rank 0 only); a checkpoint must carry all of them for the resumed run to match the uninterrupted one."""
+    out = str(tmp_path)
+    for phase in ("full", "first", "resume"):
+        mp.spawn(_run_ckpt, args=(2, _free_port(), out, phase), nprocs=2, join=True)
+    full = torch.load(os.path.join(out, "full_0.pt"))
+    for r in (0, 1):
+        assert torch.allclose(torch.load(os.path.join(out, f"resume_{r}.pt")), full, atol=1e-7), r
