@@ -22,6 +22,10 @@ class Autogm(_BaseAggregator):
         self.compat = compat
         self.gm_agg = Geomed(maxiter=maxiter, eps=eps, ftol=ftol, compat=compat)
 
+    def geometric_median_objective(self, median, points, alphas):
+        """``sum_i alpha_i * ||median - p_i||`` (reference autogm.py:33-34)."""
+        return self.gm_agg._geometric_median_objective(median, points, alphas)
+
     def aggregate(self, matrix, weights=None):
         w = gops.autogm_weights(matrix.gram(), self.lamb, self.maxiter, self.eps, self.ftol,
                                 sort_by_index=self.compat, compounding=self.compat)

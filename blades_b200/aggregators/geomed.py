@@ -39,6 +39,10 @@ class Geomed(_BaseAggregator):
         self.compat = compat
         self.last_iterations = 0
 
+    def _geometric_median_objective(self, median, points, alphas):
+        """``sum_i alpha_i * ||median - p_i||`` (reference geomed.py:61-62; the solver itself works on the Gram matrix)."""
+        return sum(float(a) * torch.linalg.norm(median - p) for a, p in zip(alphas, points))
+
     def weights_from_gram(self, G: np.ndarray, alphas=None) -> np.ndarray:
         w, self.last_iterations = gops.weiszfeld_weights(
             G, alphas, self.maxiter, self.eps, self.ftol, compounding=self.compat)

@@ -645,3 +645,35 @@ def test_resnet18_round_matches_reference(ref, tmp_path):
     err = _run_both_models(str(tmp_path), lambda: torchvision.models.resnet18(num_classes=10), lambda: resnet18(10), 1, 1,
                            n=2, bs=16)
     assert err < 5e-6, err
+
+
+def test_public_names_of_the_reference_exist_here(ref):
+    """Every public class / function (and every public method of every class) defined in the reference's modules
+    exists under the same name in the corresponding blades_b200 module."""
+    import importlib
+    import inspect
+    mods = ["utils", "client", "server", "simulator", "aggregators", "attackers", "datasets", "datasets.dataset",
+            "datasets.customdataset", "models", "models.cifar10", "models.mnist", "aggregators.torch_utils",
+            "aggregators.centeredclipping", "aggregators.autogm", "aggregators.clustering", "aggregators.fltrust",
+            "aggregators.clippedclustering", "aggregators.median", "aggregators.trimmedmean", "aggregators.byzantinesgd",
+            "attackers.alieclient", "attackers.ipmclient", "attackers.noiseclient", "attackers.labelflippingclient",
+            "attackers.signflippingclient", "models.cifar10.cctnets.utils.tokenizer", "models.cifar10.cctnets.utils.embedder",
+            "models.cifar10.cctnets.utils.helpers", "models.cifar10.cctnets.utils.stochastic_depth",
+            "models.cifar10.cctnets.utils.transformers", "models.cifar10.cctnets.registry", "models.cifar10.cctnets.cct",
+            "models.cifar10.cctnets.cvt", "models.cifar10.cctnets.vit", "models.cifar10.cctnets.text.cct",
+            "models.cifar10.cctnets.text.cvt", "models.cifar10.cctnets.text.vit", "models.cifar10.cctnets.text.transformer"]
+    problems = []
+    for name in mods:
+        rm = ref.import_module("blades." + name)
+        om = importlib.import_module("blades_b200." + name)
+        for n, v in vars(rm).items():
+            defined_here = getattr(v, "__module__", "") == rm.__name__
+            if n.startswith("_") or not defined_here or not (inspect.isclass(v) or inspect.isfunction(v)):
+                continue
+            ov = getattr(om, n, None)
+            if ov is None:
+                problems.append(f"{name}.{n}")
+            elif inspect.isclass(v):
+                problems += [f"{name}.{n}.{m}" for m, fn in vars(v).items()
+                             if inspect.isfunction(fn) and not m.startswith("__") and not hasattr(ov, m)]
+    assert not problems, problems
