@@ -86,3 +86,4 @@ def _variant(name, depth, ks, nconv, img, pe, ncls):
 for _n, _spec in _VARIANTS.items():
     globals()[_n] = _variant(_n, *_spec)
     __all__.append(_n)
+from .utils.helpers import fc_check, pe_check  # noqa: F401,E402  (import-path parity with the reference module)

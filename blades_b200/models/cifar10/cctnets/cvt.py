@@ -72,3 +72,4 @@ def _make_family(cls, prefix, depths, force_learnable=False):
 _fam = _make_family(CVT, "cvt", (2, 4, 6, 7, 8))
 globals().update(_fam)
 __all__ += [k for k in _fam if not k.startswith("_")]
+from .utils.helpers import pe_check  # noqa: F401,E402  (import-path parity with the reference module)

@@ -10,3 +10,4 @@ class TextCCT(_TextModel):
 
 globals().update(size_factories(TextCCT, "text_cct",
                                 lambda k: (max(1, (k // 2) - 1), max(1, (k // 2)))))
+from ..core import Embedder, MaskedTransformerClassifier, TextTokenizer  # noqa: F401,E402

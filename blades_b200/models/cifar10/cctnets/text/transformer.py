@@ -11,3 +11,4 @@ class TextTransformerLite(_TextModel):
 
 
 globals().update(size_factories(TextTransformerLite, "text_transformer", lambda k: (1, 0)))
+from ..core import Embedder, MaskedTransformerClassifier  # noqa: F401,E402

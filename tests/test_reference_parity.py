@@ -677,3 +677,24 @@ def test_public_names_of_the_reference_exist_here(ref):
                 problems += [f"{name}.{n}.{m}" for m, fn in vars(v).items()
                              if inspect.isfunction(fn) and not m.startswith("__") and not hasattr(ov, m)]
     assert not problems, problems
+
+
+def test_zoo_classes_accept_the_reference_constructor_arguments(ref):
+    """Direct construction (not through the factories) with the reference's own parameter names and defaults."""
+    import importlib
+    import inspect
+    for sub, cls in (("cvt", "TextCVT"), ("vit", "TextViTLite"), ("cct", "TextCCT"), ("transformer", "TextTransformerLite")):
+        r = getattr(ref.import_module(f"blades.models.cifar10.cctnets.text.{sub}"), cls)
+        o = getattr(importlib.import_module(f"blades_b200.models.cifar10.cctnets.text.{sub}"), cls)
+        rp = [p for p in inspect.signature(r.__init__).parameters.values() if p.kind.name == "POSITIONAL_OR_KEYWORD"]
+        names_o = list(inspect.signature(o.__init__).parameters)
+        assert [p.name for p in rp] == names_o[:len(rp)], (cls, names_o)
+        kw = dict(num_layers=1, num_heads=2, mlp_ratio=1)
+        variants = [dict()] + ([dict(patch_size=4, embedding_dim=64)] if sub in ("cvt", "vit") else [])
+        for extra in variants:
+            a, b = r(**kw, **extra), o(**kw, **extra)
+            assert [(k, tuple(v.shape)) for k, v in a.state_dict().items()] == \
+                   [(k, tuple(v.shape)) for k, v in b.state_dict().items()], (cls, extra)
+    for sub, names in (("cct", ["pe_check", "fc_check"]), ("cvt", ["pe_check"]), ("vit", ["pe_check", "Tokenizer", "TransformerClassifier"])):
+        om = importlib.import_module(f"blades_b200.models.cifar10.cctnets.{sub}")
+        assert all(hasattr(om, n) for n in names), sub
