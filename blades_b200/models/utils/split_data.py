@@ -6,6 +6,31 @@ import os
 from . import leaf
 
 
+def create_jsons_for(user_files, which_set, max_users, include_hierarchy, subdir='.', out_dir='.'):
+    """Split-by-user packing (reference split_data.py:16-75): ``user_files`` is a list of ``(user, num_samples,
+    file)`` -- or ``(user, hierarchy, num_samples, file)`` -- tuples; users are read from ``subdir/file`` and written
+    to ``out_dir/<stem>_<which_set>_<k>.json`` in groups of at most ``max_users``.  Returns the written paths."""
+    written, users, hier, ns, data, k = [], [], [], [], {}, 0
+    for i, t in enumerate(user_files):
+        u, h, n, f = t if include_hierarchy else (t[0], None, t[1], t[2])
+        with open(os.path.join(subdir, f)) as inf:
+            data[u] = json.load(inf)['user_data'][u]
+        users.append(u), ns.append(n)
+        if include_hierarchy:
+            hier.append(h)
+        if len(users) == max_users or i == len(user_files) - 1:
+            out = {'users': users, 'num_samples': ns, 'user_data': data}
+            if include_hierarchy:
+                out['hierarchies'] = hier
+            path = os.path.join(out_dir, '%s_%s_%d.json' % (os.path.splitext(f)[0], which_set, k))
+            os.makedirs(out_dir, exist_ok=True)
+            with open(path, 'w') as outf:
+                json.dump(out, outf)
+            written.append(path)
+            users, hier, ns, data, k = [], [], [], {}, k + 1
+    return written
+
+
 def main(argv=None):
     p = argparse.ArgumentParser()
     p.add_argument('--name', required=True, help='dataset directory containing data/all_data/*.json')

@@ -6,6 +6,30 @@ import os
 from . import leaf
 
 
+def load_data(name):
+    """``(users, num_samples)`` of every user file under ``<name>/data/all_data`` (reference stats.py:26-48)."""
+    ds = leaf.load_dir(os.path.join(name, 'data', 'all_data'))
+    return list(ds['users']), list(ds['num_samples'])
+
+
+def print_dataset_stats(name):
+    """Print the summary the reference prints (users, samples, mean / std / skew of samples per user);
+    the histogram plot is left out (reference stats.py:51-86)."""
+    import numpy as np
+    users, num_samples = load_data(name)
+    n = np.asarray(num_samples, dtype=np.float64)
+    std = n.std()
+    skew = float(((n - n.mean()) ** 3).mean() / std ** 3) if std > 0 else 0.0
+    print('####################################')
+    print('DATASET: %s' % name)
+    print('%d users' % len(users))
+    print('%d samples (total)' % int(n.sum()))
+    print('%.2f samples per user (mean)' % n.mean())
+    print('num_samples (std): %.2f' % std)
+    print('num_samples (std/mean): %.2f' % (std / n.mean() if n.mean() else 0.0))
+    print('num_samples (skewness): %.2f' % skew)
+
+
 def main(argv=None):
     p = argparse.ArgumentParser()
     p.add_argument('--name', required=True, help='dataset directory containing data/all_data/*.json')

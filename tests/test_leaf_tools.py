@@ -47,3 +47,23 @@ def test_get_cifar10_cache(tmp_path):
     with open(path, "rb") as f:
         ids, train, ids2, test = [pickle.load(f) for _ in range(4)]
     assert ids == ["0", "1", "2", "3"] and train["0"]["x"].shape == (50, 3, 32, 32) and test["3"]["y"].shape == (10,)
+
+
+def test_reference_helper_names(tmp_path, capsys):
+    """``stats.load_data / print_dataset_stats`` and ``split_data.create_jsons_for`` (names of the reference scripts)."""
+    import json
+    from blades_b200.models.utils import split_data, stats
+    root = tmp_path / "ds" / "data" / "all_data"
+    root.mkdir(parents=True)
+    users = {"u%d" % i: {"x": [[float(i)]] * (3 + i), "y": [i % 2] * (3 + i)} for i in range(5)}
+    (root / "all_data_0.json").write_text(json.dumps({"users": list(users), "num_samples": [3 + i for i in range(5)],
+                                                      "user_data": users}))
+    us, ns = stats.load_data(str(tmp_path / "ds"))
+    assert sorted(us) == sorted(users) and sum(ns) == sum(3 + i for i in range(5))
+    stats.print_dataset_stats(str(tmp_path / "ds"))
+    assert "5 users" in capsys.readouterr().out
+    files = [(u, 3 + i, "all_data_0.json") for i, u in enumerate(users)]
+    out = split_data.create_jsons_for(files, "train", 2, False, subdir=str(root), out_dir=str(tmp_path / "out"))
+    assert len(out) == 3
+    first = json.loads(open(out[0]).read())
+    assert first["users"] == ["u0", "u1"] and first["num_samples"] == [3, 4]
