@@ -125,6 +125,7 @@ class RoundEngine:
         self.kernel_launches = 0
         self._clamps = {}
         self._clamps_in_graphs = set()
+        self._shape_votes = {}      # staged input shape -> how often it occurred (tail batches are the rare ones)
         self._pf_pool = None
         self._pf_stream = None
         self._zc_plans = {}
@@ -481,6 +482,7 @@ class RoundEngine:
             except RaggedBatches as e:
                 self._train_ragged(rows, lr, e.batches)
                 return
+        self._shape_votes[tuple(X.shape)] = self._shape_votes.get(tuple(X.shape), 0) + 1
         if not self._graph_eligible(rows):
             self.last_client_losses = self._batched_step(rows, lr, X.clone(), y.clone())
             return
@@ -595,8 +597,12 @@ class RoundEngine:
             except RaggedBatches as e:
                 self._stash[(tuple(rows), 1)] = e        # the eager round picks these batches up again
                 return False
-        if "graph" in st and tuple(X.shape) != tuple(st["sx"].shape):
-            self._stash[(tuple(rows), 1)] = (X, y)       # e.g. the shorter tail batch of an epoch: not this graph
+        shape = tuple(X.shape)
+        votes = self._shape_votes[shape] = self._shape_votes.get(shape, 0) + 1
+        if ("graph" in st and shape != tuple(st["sx"].shape)) or ("graph" not in st and votes < 2):
+            # the shorter tail batch of an epoch: neither replay the captured graph with it nor spend the one
+            # whole-round capture on it -- hand the inputs to the per-step path
+            self._stash[(tuple(rows), 1)] = (X, y)
             return False
         if "graph" not in st:
             sx, sy = X.clone(), y.clone()
