@@ -389,10 +389,10 @@ class Simulator(object):
                 if not isinstance(ds, CustomTensorDataset):
                     return None
                 x, y = ds.tensors
-                if ds.transforms is not None:
-                    if not getattr(ds.transforms, "deterministic", False):
-                        return None
-                    x = torch.stack([ds.transforms(xi) for xi in x]) if len(x) else x
+                if not ds.deterministic:
+                    return None
+                if ds.transforms is not None and len(x):
+                    x = torch.stack([ds.transforms(xi) for xi in x])
                 xs.append(x), ys.append(y), lens.append(len(y))
             if min(lens) == 0:
                 return None
