@@ -121,7 +121,8 @@ def test_alie_zmax_matches_reference(ref, n, f):
     assert abs(float(got) - float(want)) < 1e-6
 
 
-def _run_both(tmp, attack, attack_kws, agg, agg_kws, rounds, local_steps, n=6, f=2, bs=8, seed=3, train_sizes=None):
+def _run_both(tmp, attack, attack_kws, agg, agg_kws, rounds, local_steps, n=6, f=2, bs=8, seed=3, train_sizes=None,
+              before_run=None):
     """Same data (the reference's cache file is read back by our BaseDataset), same seed, same API calls:
     returns (reference parameters, our parameters) after ``rounds`` rounds."""
     import pickle
@@ -134,6 +135,8 @@ def _run_both(tmp, attack, attack_kws, agg, agg_kws, rounds, local_steps, n=6, f
     run_kw = dict(global_rounds=rounds, local_steps=local_steps, validate_interval=1000, server_lr=1.0, client_lr=0.1)
     sim_r = rs.Simulator(dataset=ds_ref, num_actors=1, log_path=os.path.join(tmp, "lr"), **kw)
     m_ref = RefMLP()
+    if before_run:
+        before_run(sim_r)
     sim_r.run(m_ref, **run_kw)
 
     from blades_b200 import Simulator
@@ -151,6 +154,8 @@ def _run_both(tmp, attack, attack_kws, agg, agg_kws, rounds, local_steps, n=6, f
     ds = Same(data_root=os.path.join(tmp, "ours"), train_bs=bs, num_clients=n, seed=1)
     sim_o = Simulator(dataset=ds, log_path=os.path.join(tmp, "lo"), progress=False, **kw)
     m = MLP()
+    if before_run:
+        before_run(sim_o)
     sim_o.run(m, **run_kw)
     flat = lambda mod: torch.cat([p.detach().reshape(-1) for p in mod.parameters()])      # noqa: E731
     return flat(m_ref), flat(m)
@@ -698,3 +703,33 @@ def test_zoo_classes_accept_the_reference_constructor_arguments(ref):
     for sub, names in (("cct", ["pe_check", "fc_check"]), ("cvt", ["pe_check"]), ("vit", ["pe_check", "Tokenizer", "TransformerClassifier"])):
         om = importlib.import_module(f"blades_b200.models.cifar10.cctnets.{sub}")
         assert all(hasattr(om, n) for n in names), sub
+
+
+def test_fltrust_simulation_matches_reference(ref, tmp_path):
+    """FLTrust with one trusted client (``set_trusted_clients``) against ALIE, end to end."""
+    def trust_last(sim):
+        clients = sim.get_clients()
+        clients = list(clients.values()) if isinstance(clients, dict) else list(clients)
+        sim.set_trusted_clients([clients[-1].id()])
+    want, got = _run_both(str(tmp_path), "alie", {"num_clients": 6, "num_byzantine": 2}, "fltrust", None, 4, 1,
+                          before_run=trust_last)
+    assert (got - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("agg", ["clustering", "clippedclustering"])
+def test_clustering_simulation_matches_reference(ref, tmp_path, agg):
+    """Clustering aggregators end to end (the reference needs sklearn's removed ``affinity=`` kwarg, quirk Q7)."""
+    import sklearn.cluster as skc
+    orig = skc.AgglomerativeClustering
+
+    def compat(*a, affinity=None, **k):
+        if affinity is not None:
+            k["metric"] = affinity
+        return orig(*a, **k)
+    mod = ref.import_module(f"blades.aggregators.{agg}")
+    mod.AgglomerativeClustering = compat
+    try:
+        want, got = _run_both(str(tmp_path), "ipm", {"epsilon": 5.0}, agg, None, 4, 1)
+    finally:
+        mod.AgglomerativeClustering = orig
+    assert (got - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item())
