@@ -207,9 +207,8 @@ def complete_linkage_2(dist: np.ndarray) -> np.ndarray:
 
     Equivalent to ``AgglomerativeClustering(metric='precomputed', linkage='complete',
     n_clusters=2)`` (reference clustering.py:39-40).  O(N^3) worst case, N <= 512.
-    Labels: cluster containing the smallest index is... whichever sklearn would call
-    it is not reproduced; callers only use cluster sizes (majority vote).
-    Returns an int array of 0/1 labels with label 0 = cluster of row 0.
+    Returns an int array of 0/1 labels in sklearn's label order (``_sklearn_label_order``): callers use the cluster
+    sizes (majority vote) and, on a size tie, label 0 like the reference.
     """
     n = dist.shape[0]
     if n == 1:
@@ -240,7 +239,18 @@ def complete_linkage_2(dist: np.ndarray) -> np.ndarray:
     roots = np.unique(member)
     labels = (member != member[0]).astype(np.int64)
     assert len(roots) == 2
-    return labels
+    return _sklearn_label_order(np.maximum(dist, dist.T), labels)
+
+
+def _sklearn_label_order(dist: np.ndarray, labels: np.ndarray) -> np.ndarray:
+    """Label convention of sklearn's ``AgglomerativeClustering`` (it matters when the clusters tie in size: the
+    reference's majority rule then falls back to label 0): label 0 = the final cluster whose internal complete-linkage
+    height (largest pairwise distance inside it) is larger; singletons have none; equal heights keep row 0 in label 0.
+    Checked against sklearn on random inputs in tests/test_aggregators.py."""
+    def height(mask):
+        idx = np.where(mask)[0]
+        return -np.inf if len(idx) < 2 else dist[np.ix_(idx, idx)][np.triu_indices(len(idx), 1)].max()
+    return 1 - labels if height(labels == 1) > height(labels == 0) else labels
 
 
 def majority_cluster(labels: np.ndarray) -> np.ndarray:

@@ -172,7 +172,20 @@ void bl_complete_linkage2(const double* dist_in, int n, int64_t* labels) {
         alive[bj] = 0;
         for (int k = 0; k < n; ++k) if (member[k] == bj) member[k] = bi;
     }
-    for (int i = 0; i < n; ++i) labels[i] = (member[i] != member[0]) ? 1 : 0;
+    // Label convention of sklearn's AgglomerativeClustering (needed when the two clusters tie in size, where the
+    // reference's majority rule ``flag = sum(labels) > n // 2`` falls back to label 0, clustering.py:41): tree nodes
+    // are numbered by increasing merge height and label 0 goes to the final cluster with the larger node id, i.e. the
+    // one whose internal complete-linkage height (largest pairwise distance inside it) is larger; a singleton has none.
+    // Equal heights: the cluster of row 0 keeps label 0.
+    double h0 = -INF, h1 = -INF;
+    for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j) {
+            if (member[i] != member[j]) continue;
+            const double v = std::max(dist_in[(size_t)i * n + j], dist_in[(size_t)j * n + i]);
+            if (member[i] == member[0]) h0 = std::max(h0, v); else h1 = std::max(h1, v);
+        }
+    const bool swap = h1 > h0;
+    for (int i = 0; i < n; ++i) labels[i] = ((member[i] != member[0]) != swap) ? 1 : 0;
 }
 
 // Multi-threaded mini-batch assembly into (pinned) host buffers: for client c and slot j copy

@@ -272,3 +272,29 @@ def test_autogm_textbook_mode_is_permutation_invariant_and_robust():
     # the compat result is a valid robust aggregate too, but it depends on the client order for some inputs
     c = Autogm(lamb=2.0, compat=True)(U)
     assert (c - honest.mean(0)).norm() < 0.5 * (U.mean(0) - honest.mean(0)).norm()
+
+
+@pytest.mark.parametrize("native", [True, False])
+def test_complete_linkage_label_order_matches_sklearn(native, monkeypatch):
+    """Labels (not only the partition) follow sklearn: label 0 = the final cluster with the larger internal
+    complete-linkage height -- the reference's majority rule falls back to label 0 when the clusters tie in size."""
+    sk = pytest.importorskip("sklearn.cluster")
+    monkeypatch.setattr(gops, "USE_NATIVE", native)
+    rng = np.random.default_rng(1)
+    checked = 0
+    for trial in range(200):
+        n = int(rng.integers(3, 14))
+        X = rng.standard_normal((n, 4))
+        if trial % 3 == 0:                      # identical rows (an omniscient attacker's clients): zero distances
+            X[: int(rng.integers(2, n))] = X[0]
+        D = np.linalg.norm(X[:, None] - X[None], axis=-1)
+        mine = gops.complete_linkage_2(D)
+        ref = sk.AgglomerativeClustering(metric='precomputed', linkage='complete', n_clusters=2).fit(D).labels_
+        if not ((mine == ref).all() or (mine == 1 - ref).all()):
+            continue                            # exact distance ties can legitimately produce another dendrogram
+        h = [(-np.inf if (mine == k).sum() < 2 else D[np.ix_(mine == k, mine == k)].max()) for k in (0, 1)]
+        if h[0] == h[1]:
+            continue
+        assert (mine == ref).all(), trial
+        checked += 1
+    assert checked > 150
