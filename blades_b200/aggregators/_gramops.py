@@ -203,13 +203,19 @@ def cosine_matrix(G: np.ndarray) -> np.ndarray:
 
 
 def complete_linkage_2(dist: np.ndarray) -> np.ndarray:
-    """Two-cluster complete-linkage agglomeration on a precomputed 'distance' matrix.
+    """Two-cluster complete-linkage agglomeration on a precomputed 'distance' matrix, LABEL FOR LABEL what
+    ``AgglomerativeClustering(metric='precomputed', linkage='complete', n_clusters=2)`` returns (reference
+    clustering.py:39-40) -- including inputs full of exact ties (the identical rows of ALIE / IPM attackers, the
+    similarity-as-distance matrices of quirk Q7), where the dendrogram depends on the merge order, and including the
+    label numbering, which the reference's majority rule falls back to when the clusters tie in size.
 
-    Equivalent to ``AgglomerativeClustering(metric='precomputed', linkage='complete',
-    n_clusters=2)`` (reference clustering.py:39-40).  O(N^3) worst case, N <= 512.
-    Returns an int array of 0/1 labels in sklearn's label order (``_sklearn_label_order``): callers use the cluster
-    sizes (majority vote) and, on a size tie, label 0 like the reference.
-    """
+    That requires following sklearn -> scipy step by step: (1) only the upper triangle of the matrix is used;
+    (2) scipy's NN-chain algorithm produces the merges (chain started at the first live cluster, ``<`` comparisons in
+    index order, the previous chain element preferred on ties, the merged cluster stored under the larger index);
+    (3) the merges are STABLE-sorted by height and relabelled by union-find, node ids growing in that order;
+    (4) sklearn's ``_hc_cut`` gives label 0 to the child of the root with the larger node id.
+    O(N^2) memory, O(N^2)..O(N^3) time, N <= 512.  ``tests/test_aggregators.py`` checks 600 random matrices (ties,
+    duplicates, negative 'distances') against sklearn."""
     n = dist.shape[0]
     if n == 1:
         return np.zeros(1, dtype=np.int64)
@@ -217,40 +223,65 @@ def complete_linkage_2(dist: np.ndarray) -> np.ndarray:
     if nat is not None:
         return nat.complete_linkage2(dist)
     D = np.array(dist, dtype=np.float64, copy=True)
-    D = np.maximum(D, D.T)            # symmetrise (reference matrices are symmetric)
-    np.fill_diagonal(D, np.inf)
-    alive = np.ones(n, dtype=bool)
-    member = np.arange(n)
-    n_clusters = n
-    while n_clusters > 2:
-        sub = np.where(alive[:, None] & alive[None, :], D, np.inf)
-        flat = int(np.argmin(sub))
-        i, j = divmod(flat, n)
-        if i > j:
-            i, j = j, i
-        # merge j into i; complete linkage = max of the two rows
-        merged = np.maximum(D[i], D[j])
-        D[i, :] = merged
-        D[:, i] = merged
-        D[i, i] = np.inf
-        alive[j] = False
-        member[member == j] = i
-        n_clusters -= 1
-    roots = np.unique(member)
-    labels = (member != member[0]).astype(np.int64)
-    assert len(roots) == 2
-    return _sklearn_label_order(np.maximum(dist, dist.T), labels)
+    iu = np.triu_indices(n, 1)
+    D[(iu[1], iu[0])] = D[iu]
+    size = np.ones(n, dtype=np.int64)
+    chain = np.zeros(n, dtype=np.int64)
+    clen = 0
+    merges = np.zeros((n - 1, 3))
+    for k in range(n - 1):
+        if clen == 0:
+            clen = 1
+            chain[0] = int(np.nonzero(size > 0)[0][0])
+        while True:
+            x = int(chain[clen - 1])
+            if clen > 1:
+                y = int(chain[clen - 2])
+                cur = D[x, y]
+            else:
+                y, cur = -1, np.inf
+            row = np.where((size > 0) & (np.arange(n) != x), D[x], np.inf)
+            i = int(np.argmin(row))                      # first strict minimum in index order
+            if row[i] < cur:
+                cur, y = row[i], i
+            if clen > 1 and y == chain[clen - 2]:
+                break
+            chain[clen] = y
+            clen += 1
+        clen -= 2
+        if x > y:
+            x, y = y, x
+        merges[k] = (x, y, cur)
+        size[y] += size[x]
+        size[x] = 0
+        upd = np.maximum(D[:, x], D[:, y])
+        live = (size > 0) & (np.arange(n) != y)
+        D[live, y] = upd[live]
+        D[y, live] = upd[live]
+    merges = merges[np.argsort(merges[:, 2], kind="mergesort")]
+    parent = np.arange(2 * n - 1)
 
-
-def _sklearn_label_order(dist: np.ndarray, labels: np.ndarray) -> np.ndarray:
-    """Label convention of sklearn's ``AgglomerativeClustering`` (it matters when the clusters tie in size: the
-    reference's majority rule then falls back to label 0): label 0 = the final cluster whose internal complete-linkage
-    height (largest pairwise distance inside it) is larger; singletons have none; equal heights keep row 0 in label 0.
-    Checked against sklearn on random inputs in tests/test_aggregators.py."""
-    def height(mask):
-        idx = np.where(mask)[0]
-        return -np.inf if len(idx) < 2 else dist[np.ix_(idx, idx)][np.triu_indices(len(idx), 1)].max()
-    return 1 - labels if height(labels == 1) > height(labels == 0) else labels
+    def find(a):
+        r = a
+        while parent[r] != r:
+            r = parent[r]
+        while parent[a] != r:
+            parent[a], a = r, parent[a]
+        return r
+    children = np.zeros((n - 1, 2), dtype=np.int64)
+    for i in range(n - 1):
+        xr, yr = find(int(merges[i, 0])), find(int(merges[i, 1]))
+        children[i] = (min(xr, yr), max(xr, yr))
+        parent[xr] = parent[yr] = n + i
+    labels = np.zeros(n, dtype=np.int64)
+    stack = [int(children[-1].min())]                   # the root's child with the SMALLER node id is cluster 1
+    while stack:
+        a = stack.pop()
+        if a < n:
+            labels[a] = 1
+        else:
+            stack.extend(int(c) for c in children[a - n])
+    return labels
 
 
 def majority_cluster(labels: np.ndarray) -> np.ndarray:

@@ -138,54 +138,76 @@ void bl_centered_clip(const double* G_aug, int n, double tau, int n_iter, double
 // Two-cluster complete-linkage agglomeration on a symmetric 'distance' matrix; labels[i] in {0,1},
 // label 0 = cluster of row 0.
 void bl_complete_linkage2(const double* dist_in, int n, int64_t* labels) {
+    // Label for label what sklearn's AgglomerativeClustering(metric='precomputed', linkage='complete', n_clusters=2)
+    // returns (see aggregators/_gramops.py::complete_linkage_2 for the why): upper triangle only, scipy's NN-chain
+    // merge order, stable sort of the merges by height, union-find relabelling, label 0 = the root's child with the
+    // larger node id.
     if (n <= 0) return;
     if (n == 1) { labels[0] = 0; return; }
     const double INF = std::numeric_limits<double>::infinity();
     std::vector<double> D((size_t)n * n);
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j)
-            D[(size_t)i * n + j] = (i == j) ? INF : std::max(dist_in[(size_t)i * n + j], dist_in[(size_t)j * n + i]);
-    std::vector<char> alive(n, 1);
-    std::vector<int> member(n);
-    std::iota(member.begin(), member.end(), 0);
-    for (int clusters = n; clusters > 2; --clusters) {
-        double best = INF;
-        int bi = -1, bj = -1;
-        for (int i = 0; i < n; ++i) {
-            if (!alive[i]) continue;
-            for (int j = 0; j < n; ++j) {           // row-major argmin: first minimum wins (numpy order)
-                if (!alive[j] || j == i) continue;
-                const double v = D[(size_t)i * n + j];
-                if (v < best) { best = v; bi = i; bj = j; }
+            D[(size_t)i * n + j] = (i == j) ? 0.0 : (i < j ? dist_in[(size_t)i * n + j] : dist_in[(size_t)j * n + i]);
+    std::vector<int> size(n, 1), chain(n, 0);
+    int clen = 0;
+    struct Merge { int x, y; double h; int order; };
+    std::vector<Merge> merges(n - 1);
+    for (int k = 0; k < n - 1; ++k) {
+        if (clen == 0) {
+            clen = 1;
+            for (int i = 0; i < n; ++i) if (size[i] > 0) { chain[0] = i; break; }
+        }
+        int x, y;
+        double cur;
+        while (true) {
+            x = chain[clen - 1];
+            if (clen > 1) { y = chain[clen - 2]; cur = D[(size_t)x * n + y]; }
+            else { y = -1; cur = INF; }
+            for (int i = 0; i < n; ++i) {
+                if (size[i] == 0 || i == x) continue;
+                const double d = D[(size_t)x * n + i];
+                if (d < cur) { cur = d; y = i; }
             }
+            if (clen > 1 && y == chain[clen - 2]) break;
+            chain[clen++] = y;
         }
-        if (bi < 0) {                                // all remaining distances infinite: merge first two alive
-            for (int i = 0; i < n && bj < 0; ++i) if (alive[i]) { if (bi < 0) bi = i; else bj = i; }
+        clen -= 2;
+        if (x > y) std::swap(x, y);
+        merges[k] = {x, y, cur, k};
+        size[y] += size[x];
+        size[x] = 0;
+        for (int i = 0; i < n; ++i) {
+            if (size[i] == 0 || i == y) continue;
+            const double v = std::max(D[(size_t)i * n + x], D[(size_t)i * n + y]);
+            D[(size_t)i * n + y] = v;
+            D[(size_t)y * n + i] = v;
         }
-        if (bi > bj) std::swap(bi, bj);
-        for (int k = 0; k < n; ++k) {
-            const double v = std::max(D[(size_t)bi * n + k], D[(size_t)bj * n + k]);
-            D[(size_t)bi * n + k] = v;
-            D[(size_t)k * n + bi] = v;
-        }
-        D[(size_t)bi * n + bi] = INF;
-        alive[bj] = 0;
-        for (int k = 0; k < n; ++k) if (member[k] == bj) member[k] = bi;
     }
-    // Label convention of sklearn's AgglomerativeClustering (needed when the two clusters tie in size, where the
-    // reference's majority rule ``flag = sum(labels) > n // 2`` falls back to label 0, clustering.py:41): tree nodes
-    // are numbered by increasing merge height and label 0 goes to the final cluster with the larger node id, i.e. the
-    // one whose internal complete-linkage height (largest pairwise distance inside it) is larger; a singleton has none.
-    // Equal heights: the cluster of row 0 keeps label 0.
-    double h0 = -INF, h1 = -INF;
-    for (int i = 0; i < n; ++i)
-        for (int j = i + 1; j < n; ++j) {
-            if (member[i] != member[j]) continue;
-            const double v = std::max(dist_in[(size_t)i * n + j], dist_in[(size_t)j * n + i]);
-            if (member[i] == member[0]) h0 = std::max(h0, v); else h1 = std::max(h1, v);
-        }
-    const bool swap = h1 > h0;
-    for (int i = 0; i < n; ++i) labels[i] = ((member[i] != member[0]) != swap) ? 1 : 0;
+    std::stable_sort(merges.begin(), merges.end(), [](const Merge& a, const Merge& b) { return a.h < b.h; });
+    std::vector<int> parent(2 * n - 1);
+    std::iota(parent.begin(), parent.end(), 0);
+    auto find = [&](int a) {
+        int r = a;
+        while (parent[r] != r) r = parent[r];
+        while (parent[a] != r) { const int nx = parent[a]; parent[a] = r; a = nx; }
+        return r;
+    };
+    std::vector<int> child0(n - 1), child1(n - 1);
+    for (int i = 0; i < n - 1; ++i) {
+        const int xr = find(merges[i].x), yr = find(merges[i].y);
+        child0[i] = std::min(xr, yr);
+        child1[i] = std::max(xr, yr);
+        parent[xr] = parent[yr] = n + i;
+    }
+    for (int i = 0; i < n; ++i) labels[i] = 0;
+    std::vector<int> stack{child0[n - 2]};          // the root's child with the smaller node id is cluster 1
+    while (!stack.empty()) {
+        const int a = stack.back();
+        stack.pop_back();
+        if (a < n) labels[a] = 1;
+        else { stack.push_back(child0[a - n]); stack.push_back(child1[a - n]); }
+    }
 }
 
 // Multi-threaded mini-batch assembly into (pinned) host buffers: for client c and slot j copy
