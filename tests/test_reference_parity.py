@@ -785,3 +785,35 @@ def test_constructed_optimizers_and_schedulers_match_reference(ref, tmp_path, se
         assert err.max().item() < 0.01
     else:
         assert err.max().item() <= 1e-5 * max(1.0, want.abs().max().item())
+
+
+def test_fuzzed_clustering_simulations_match_reference(ref, tmp_path):
+    """Clustering / Clippedclustering under attackers that submit IDENTICAL rows (IPM, ALIE) in numbers up to half of
+    the clients: exact ties in the linkage and ties in the cluster sizes -- the global models still agree."""
+    import random as _random
+    import sklearn.cluster as skc
+    orig = skc.AgglomerativeClustering
+
+    def compat(*a, affinity=None, **k):
+        if affinity is not None:
+            k["metric"] = affinity
+        return orig(*a, **k)
+    mods = [ref.import_module(f"blades.aggregators.{a}") for a in ("clustering", "clippedclustering")]
+    for m in mods:
+        m.AgglomerativeClustering = compat
+    rng = _random.Random(5)
+    try:
+        for it in range(8):
+            n = rng.choice([4, 6, 8, 10])
+            f = rng.choice([n // 2, n // 2 - 1, 1])
+            atk, akw = rng.choice([("ipm", {"epsilon": rng.choice([0.5, 5.0, 100.0])}),
+                                   ("alie", {"num_clients": n, "num_byzantine": f}), ("signflipping", None)])
+            agg, gkw = rng.choice([("clustering", None), ("clippedclustering", None), ("clippedclustering", {"tau": 1.0})])
+            ls, rounds = rng.choice([1, 2]), 3
+            want, got = _run_both(str(tmp_path / str(it)), atk, akw, agg, gkw, rounds, ls, n=n, f=f, bs=8,
+                                  seed=rng.randint(0, 99))
+            err = (got - want).abs().max().item()
+            assert err <= 1e-5 * max(1.0, want.abs().max().item()), (it, n, f, atk, agg, err)
+    finally:
+        for m in mods:
+            m.AgglomerativeClustering = orig
