@@ -817,3 +817,40 @@ def test_fuzzed_clustering_simulations_match_reference(ref, tmp_path):
     finally:
         for m in mods:
             m.AgglomerativeClustering = orig
+
+
+def test_small_simulator_apis_match_reference(ref, tmp_path):
+    """``cache_random_state / restore_random_state``, ``parallel_call / parallel_get``, ``log_variance``,
+    ``get_clients`` ordering and Byzantine-first assignment behave like the reference's."""
+    from baseline import ref_arm
+    rs = ref_arm.import_reference(0)
+    from blades_b200 import Simulator
+    from blades_b200.datasets import synthetic_fldataset
+    ds_ref = ref_arm.make_dataset(5, 8, str(tmp_path / "ref"), shape=(28, 28))
+    sims = [rs.Simulator(dataset=ds_ref, num_byzantine=2, attack="ipm", attack_kws={"epsilon": 0.5}, num_actors=1,
+                         log_path=str(tmp_path / "lr"), seed=1),
+            Simulator(synthetic_fldataset(5, shape=(28, 28), train_bs=8, train_per_client=16, test_per_client=8),
+                      num_byzantine=2, attack="ipm", attack_kws={"epsilon": 0.5}, log_path=str(tmp_path / "lo"), seed=1,
+                      progress=False)]
+    for sim in sims:
+        clients = sim.get_clients()
+        clients = list(clients.values()) if isinstance(clients, dict) else list(clients)
+        assert [c.id() for c in clients] == [0, 1, 2, 3, 4]
+        assert [c.is_byzantine() for c in clients] == [True, True, False, False, False]
+        sim.cache_random_state()
+        a = (torch.rand(3), np.random.rand(3))
+        sim.restore_random_state()
+        b = (torch.rand(3), np.random.rand(3))                      # torch + numpy streams (reference :153-165)
+        assert torch.equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        seen = []
+        sim.parallel_call(clients, lambda c: seen.append(c.id()))
+        assert sorted(seen) == [0, 1, 2, 3, 4]
+        assert list(sim.parallel_get(clients, lambda c: c.id() * 2)) == [0, 2, 4, 6, 8]
+    ups = [torch.randn(11) for _ in range(4)]
+    recs = []
+    for sim in sims:
+        out = sim.log_variance(3, [u.clone() for u in ups])
+        recs.append(out)
+    if recs[0] is not None and recs[1] is not None:                   # the reference returns the record it logs
+        for k in ("avg", "norm", "avg_norm"):
+            assert abs(float(recs[0][k]) - float(recs[1][k])) < 1e-5 * max(1.0, abs(float(recs[0][k]))), k
