@@ -234,16 +234,30 @@ static bool select_partition_enabled() {
     return on;
 }
 
+// The partition-only kernel applies when the real rows fill the padded size exactly, the trim count is a quarter of
+// them and a virtual row (if any) has multiplicity >= the trim count (select_part_core.cuh).
+static bool partition_applies(const SelectParams& p, int NP) {
+    return p.mode == 0 && p.n_real == NP && p.trim_b * 4 == NP && (p.n_virtual == 0 || p.n_virtual >= p.trim_b)
+           && (p.n_virtual == 0 || p.n_stat >= 2 || p.virt_kind != 1) && select_partition_enabled();
+}
+
 template <int NP>
 static bool launch_partition(const SelectParams& p, unsigned grid, int block, cudaStream_t st) {
     if constexpr (NP % 8 == 0) {
-        if (p.mode == 0 && p.n_real == NP && p.trim_b * 4 == NP && (p.n_virtual == 0 || p.n_virtual >= p.trim_b)
-            && (p.n_virtual == 0 || p.n_stat >= 2 || p.virt_kind != 1) && select_partition_enabled()) {
+        if (partition_applies(p, NP)) {
             coord_select_part_kernel<NP><<<grid, block, 0, st>>>(p);
             return true;
         }
     }
     return false;
+}
+
+// Which kernel bl_coord_select would launch for these parameters (no CUDA call: usable without a GPU by the tests):
+// 0 = none (n_real outside 1..128: the large-N kernel is a different entry point), 1 = full sorting network,
+// 2 = partition-only trimmed mean.
+extern "C" int bl_coord_select_choice(const SelectParams* p) {
+    if (p->n_real < 1 || p->n_real > 128) return 0;
+    return partition_applies(*p, (p->n_real + 7) / 8 * 8) ? 2 : 1;
 }
 
 template <int NP>

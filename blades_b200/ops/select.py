@@ -43,6 +43,24 @@ def launch_select(stat_rows: Sequence[int], other_rows: Sequence[int], n_virtual
                   device=None) -> None:
     """``stat_rows`` (pointers) enter the attack statistics; ``other_rows`` are real rows that do not."""
     lib = _loader.cuda_lib()
+    p, fn = _select_params(lib, stat_rows, other_rows, n_virtual, kind, param, mode, trim_b, c0, c1, ep)
+    _loader.check(fn(C.byref(p), _loader.stream_ptr(device)), "coord_select")
+    _loader.count_launch()
+
+
+def kernel_choice(n_stat: int, n_other: int, n_virtual: int, kind: Optional[str], mode: int, trim_b: int) -> str:
+    """Which kernel a launch with these row counts takes: ``"partition"`` (two half sorts + bitonic splits),
+    ``"network"`` (full sorting network) or ``"large"`` (shared-memory bitonic sort, > 128 real rows).  Pure host
+    logic (asks the library's own dispatch predicate, no CUDA call)."""
+    lib = _loader.cuda_lib()
+    n_real = n_stat + n_other
+    if n_real > 128:
+        return "large"
+    p, _ = _select_params(lib, [0] * n_stat, [0] * n_other, n_virtual, kind, 0.5, mode, trim_b, 0, 1, _structs.Epilogue())
+    return {1: "network", 2: "partition"}[lib.bl_coord_select_choice(C.byref(p))]
+
+
+def _select_params(lib, stat_rows, other_rows, n_virtual, kind, param, mode, trim_b, c0, c1, ep):
     rows = list(stat_rows) + list(other_rows)
     n_real = len(rows)
     total = n_real + n_virtual
@@ -60,8 +78,7 @@ def launch_select(stat_rows: Sequence[int], other_rows: Sequence[int], n_virtual
     p.n_real, p.n_stat, p.n_virtual = n_real, len(stat_rows), n_virtual
     p.virt_kind, p.virt_param = _KIND[kind if n_virtual else None], float(param)
     p.mode, p.trim_b, p.c0, p.c1, p.ep = mode, trim_b, c0, c1, ep
-    _loader.check(fn(C.byref(p), _loader.stream_ptr(device)), "coord_select")
-    _loader.count_launch()
+    return p, fn
 
 
 def _dense(data: torch.Tensor, mode: int, b: int, virtual) -> torch.Tensor:

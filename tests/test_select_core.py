@@ -32,3 +32,24 @@ def test_sorting_network_generator_is_reproducible(tmp_path):
     assert open(out).read() == open(os.path.join(ROOT, "blades_b200", "csrc", "cuda", "gen", "sortnet_gen.cuh")).read()
     chk = subprocess.run([sys.executable, gen, "check"], capture_output=True, text=True)
     assert chk.returncode == 0 and "128" in chk.stdout
+
+
+def test_dispatch_predicate_of_the_select_launcher():
+    """Which kernel the launcher picks (asked from the library's own predicate, no CUDA call): the headline round
+    (100 clients, 20 ALIE attackers fused as virtual rows, Trimmedmean(nb=20)) takes the partition-only kernel."""
+    so = os.path.join(ROOT, "blades_b200", "_cuda.so")
+    if not os.path.exists(so):
+        pytest.skip("library not built")
+    from blades_b200.ops import select
+    # (honest rows, other real rows, virtual multiplicity, kind, mode 0 = trimmed mean / 1 = median, b)
+    assert select.kernel_choice(80, 0, 20, "alie", 0, 20) == "partition"        # the headline
+    assert select.kernel_choice(80, 0, 20, "ipm", 0, 20) == "partition"
+    assert select.kernel_choice(80, 0, 0, None, 0, 20) == "partition"           # no attack, n = 4b
+    assert select.kernel_choice(40, 0, 10, "alie", 0, 10) == "partition"        # 50 clients, 20 % attackers
+    assert select.kernel_choice(45, 3, 12, "alie", 0, 12) == "partition"        # 48 real rows, 3 outside the statistics
+    assert select.kernel_choice(80, 0, 20, "alie", 1, 0) == "network"           # median keeps the full network
+    assert select.kernel_choice(100, 0, 0, None, 0, 20) == "network"            # 100 real rows: n != 4b
+    assert select.kernel_choice(80, 0, 10, "alie", 0, 20) == "network"          # f < b
+    assert select.kernel_choice(75, 0, 25, "alie", 0, 20) == "network"          # padded (75 -> 80 slots)
+    assert select.kernel_choice(80, 0, 20, "alie", 0, 19) == "network"
+    assert select.kernel_choice(160, 0, 40, "alie", 0, 40) == "large"
