@@ -496,6 +496,20 @@ void bn_cl_set_attrs() {
 }
 }  // namespace
 
+// The plan the launchers below would use (no CUDA call: usable without a GPU by the tests).  ``staged`` = 1 for
+// the forward (x tile), 2 for the backward (xhat and gy tiles).  Returns the cluster size S (0 = plain kernel) and
+// writes the channel quads per tile and the dynamic shared memory per CTA.
+extern "C" int bl_client_bn_cluster_plan(int n, int B, int C, int HW, int staged, int* quads_out, long long* smem_out) {
+    ClientBNParams p = {};
+    p.n = n; p.B = B; p.C = C; p.HW = HW;
+    int S = 0, quads = 0;
+    size_t smem = 0;
+    if (C % 4 != 0 || !bn_cl_plan(&p, staged, &S, &quads, &smem)) return 0;
+    if (quads_out) *quads_out = quads;
+    if (smem_out) *smem_out = (long long)smem;
+    return S;
+}
+
 extern "C" int bl_client_bn_nhwc_fwd(const ClientBNParams* p, void* stream) {
     if (p->C % 4 != 0) return -1;
     int S, quads; size_t smem;

@@ -53,3 +53,28 @@ def test_dispatch_predicate_of_the_select_launcher():
     assert select.kernel_choice(75, 0, 25, "alie", 0, 20) == "network"          # padded (75 -> 80 slots)
     assert select.kernel_choice(80, 0, 20, "alie", 0, 19) == "network"
     assert select.kernel_choice(160, 0, 40, "alie", 0, 40) == "large"
+
+
+def test_batchnorm_cluster_plan():
+    """The measured dispatch of the per-client BatchNorm kernels (cluster / DSMEM form vs the plain one), asked from
+    the library without a GPU: ResNet-18 layers at 100 clients x batch 32."""
+    import ctypes as C
+    so = os.path.join(ROOT, "blades_b200", "_cuda.so")
+    if not os.path.exists(so):
+        pytest.skip("library not built")
+    from blades_b200.ops import _loader
+    lib = _loader.cuda_lib()
+
+    def plan(n, B, Cc, HW, staged):
+        q, sm = C.c_int(0), C.c_longlong(0)
+        S = lib.bl_client_bn_cluster_plan(n, B, Cc, HW, staged, C.byref(q), C.byref(sm))
+        return (S, q.value, sm.value) if S else None
+    assert plan(100, 32, 64, 256, 1) == (8, 4, 64 * 1024)        # stem forward: 8-CTA clusters, 16-channel tiles
+    assert plan(100, 32, 64, 256, 2) is None                     # stem backward would need 128 KB per CTA: plain kernel
+    assert plan(100, 32, 64, 64, 1) == (4, 8, 64 * 1024)         # layer1 forward
+    assert plan(100, 32, 64, 64, 2) == (8, 8, 64 * 1024)         # layer1 backward
+    assert plan(100, 32, 128, 16, 1) is None                     # R = 512 and shorter: plain kernel measured faster
+    assert plan(100, 32, 256, 4, 2) is None
+    S, q, sm = plan(1, 32, 64, 256, 1)                           # fedavg visit (one client): still split 8 ways
+    assert S == 8 and sm <= 64 * 1024
+    assert plan(4, 33, 64, 31, 1) is None or plan(4, 33, 64, 31, 1)[2] <= 64 * 1024      # odd sizes never exceed 64 KB
