@@ -626,6 +626,8 @@ class RoundEngine:
             _loader.count_launch(-n_native)
             if not ok:
                 st["disabled"] = True
+                if self.prestaged is None:
+                    self._stash[(tuple(rows), 1)] = (X, y)      # the eager round trains on these inputs
                 return False
             st.update(graph=graph, sx=sx, sy=sy, losses=losses, agg=agg, n_native=n_native)
         st["sx"].copy_(X, non_blocking=True)
