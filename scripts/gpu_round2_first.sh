@@ -16,3 +16,5 @@ done
 timeout 200 python scripts/profile_round.py > gpurun_out/round_kernels.txt 2>&1; head -24 gpurun_out/round_kernels.txt | cut -c1-150
 # 4. one ncu capture of the new select kernel
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"coord_select_part" -c 1 -o gpurun_out/prof_select_part python scripts/run_kernels_once.py > gpurun_out/ncu_select_part.log 2>&1; tail -2 gpurun_out/ncu_select_part.log
+# (multi-GPU follow-up, separate call:  gpurun --gpus 8 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 8
+#   --master-addr 127.0.0.1 scripts/phase_times_multigpu.py; python -m torch.distributed.run ... bench.py --gpus 8')
