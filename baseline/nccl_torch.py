@@ -163,7 +163,8 @@ def run_baseline(args, CONFIGS) -> dict:
     clocks = sampler.stop() if world.rank == 0 else {}
     if world.rank != 0:
         return {}
-    return {"metric": "FL rounds/sec (device-timed, max over ranks)", "value": args.steps / (ms / 1e3),
+    return {"metric": "FL rounds/sec", "timing": "device (CUDA events around the K rounds, max over ranks)",
+            "value": args.steps / (ms / 1e3),
             "unit": "rounds/s", "n_gpus": world.size, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "fp32 (torch defaults: TF32 convs)", "data": "synthetic", "impl": "baseline-nccl-torch",

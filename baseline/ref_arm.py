@@ -159,12 +159,13 @@ def make_dataset(num_clients: int, batch: int, data_root: str, shape=(3, 32, 32)
 
 
 def run(steps: int, warmup: int, gpus: int = 1, clients: int = 100, byzantine: int = 20, batch: int = 32,
-        model_name: str = "resnet18", budget_s: float = 420.0) -> dict:
+        model_name: str = "resnet18", budget_s: float = 420.0, soft_deadline_s: float = 1300.0) -> dict:
     """Time the reference's own round loop.  ``Simulator.run`` returns its per-round wall times (reference
     ``simulator.py:452-457``; every round ends with the CPU-side aggregation + server step, so the wall clock is the
     round time).  The reference round is minutes long on this config (CPU aggregation of a 4.5 GB update matrix), so
-    the number of rounds is bounded by ``budget_s``: one probe round (doubles as warm-up), then as many timed rounds
-    as fit, at least one, at most ``steps``."""
+    the number of rounds is bounded: one warm-up round, then at least three timed rounds (more while ``budget_s``
+    lasts, at most ``steps``; only ``soft_deadline_s`` can cut the minimum short).  The counts actually run are
+    reported."""
     import torch
     rs = import_reference(gpus)
     use_cuda = torch.cuda.is_available()
@@ -189,21 +190,23 @@ def run(steps: int, warmup: int, gpus: int = 1, clients: int = 100, byzantine: i
     t0 = time.time()
     probe = sim.run(model(), global_rounds=1, **kw)               # warm-up / probe round
     per_round = max(probe[0], 1e-3)
+    req = {"steps": steps, "warmup": warmup, "budget_s": budget_s, "soft_deadline_s": soft_deadline_s}
+    # After the warm-up round: at least ``MIN_TIMED`` timed rounds whatever the budget says (a ratio against a single
+    # un-warmed round is not a measurement), more while the budget lasts, never more than ``steps``.  Only the soft
+    # deadline (the caller's hard limit minus a margin) can cut the minimum short.
+    MIN_TIMED = 3
     left = budget_s - (time.time() - t0)
-    req = {"steps": steps, "warmup": warmup, "budget_s": budget_s}
-    if left < 1.2 * per_round:
-        # not even one more round fits: the probe round IS the measurement (a minutes-long round dominated by the
-        # CPU-side attack + aggregation; one-time CUDA/cuDNN initialisation is a second or two of it)
-        return {"value": 1.0 / per_round, "ms_per_step": 1e3 * per_round, "steps": 1, "warmup": 0, "requested": req,
-                "round_s": [round(per_round, 3)], "note": "single un-warmed round: time budget exhausted"}
-    fit = int(left / per_round)
-    extra_warm = max(0, min(warmup - 1, fit - steps))
-    k = max(1, min(steps, fit - extra_warm))
-    times = sim.run(model(), global_rounds=extra_warm + k, **kw)
-    timed = times[extra_warm:]
-    sec = sum(timed)
-    return {"value": len(timed) / sec, "ms_per_step": 1e3 * sec / len(timed), "steps": len(timed),
-            "warmup": 1 + extra_warm, "requested": req, "round_s": [round(t, 3) for t in [probe[0]] + list(times)]}
+    k = max(MIN_TIMED, min(steps, int(left / per_round)))
+    k = min(k, steps)
+    room = int((soft_deadline_s - (time.time() - t0)) / (1.15 * per_round))
+    note = ""
+    if room < k:
+        note = f"soft deadline: {max(room, 1)} timed round(s) instead of {k}"
+        k = max(room, 1)
+    times = sim.run(model(), global_rounds=k, **kw)
+    sec = sum(times)
+    return {"value": len(times) / sec, "ms_per_step": 1e3 * sec / len(times), "steps": len(times),
+            "warmup": 1, "requested": req, "round_s": [round(t, 3) for t in [probe[0]] + list(times)], "note": note}
 
 
 if __name__ == "__main__":
@@ -217,7 +220,8 @@ if __name__ == "__main__":
     ap.add_argument("--byzantine", type=int, default=20)
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--model", default="resnet18")
-    ap.add_argument("--budget", type=float, default=300.0)
+    ap.add_argument("--budget", type=float, default=420.0)
+    ap.add_argument("--soft-deadline", type=float, default=1300.0)
     a = ap.parse_args()
-    out = run(a.steps, a.warmup, a.gpus, a.clients, a.byzantine, a.batch, a.model, a.budget)
+    out = run(a.steps, a.warmup, a.gpus, a.clients, a.byzantine, a.batch, a.model, a.budget, a.soft_deadline)
     print("REF_RESULT " + json.dumps(out), flush=True)

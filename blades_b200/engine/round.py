@@ -94,6 +94,11 @@ def _overrides(obj, name: str, base=BladesClient) -> bool:
     return getattr(type(obj), name) is not getattr(base, name)
 
 
+def _default_ce(fn) -> bool:
+    return (type(fn) is nn.CrossEntropyLoss and fn.weight is None and fn.reduction == "mean"
+            and fn.label_smoothing == 0.0 and fn.ignore_index == -100)
+
+
 def _fusable_classes():
     from ..attackers.alieclient import AlieClient
     from ..attackers.ipmclient import IpmClient
@@ -145,6 +150,7 @@ class RoundEngine:
         #: clients per fused forward/backward (0 = all local clients at once)
         self.max_batched_clients = int(os.environ.get("BLADES_MAX_BATCHED_CLIENTS", "0"))
         self._sliced_graphs = {}
+        self._eager_slice_bufs = {}
         self._workers = []
         self._slice_copied = {}
         self._round_graphs = {}     # (client lr, server lr) -> captured whole-round graph state
@@ -210,9 +216,13 @@ class RoundEngine:
 
     # ------------------------------------------------------------------ training
     def _stock_for_batching(self, c: BladesClient) -> bool:
-        return not (_overrides(c, "local_training") or _overrides(c, "on_train_round_begin")
-                    or _overrides(c, "on_train_round_end") or _overrides(c, "set_para")
-                    or _overrides(c, "_post_backward") and not hasattr(c, "grad_sign"))
+        """The fused passes hard-wire mean cross-entropy (clamped per client): anything else -- a custom loss callable
+        (``Simulator.run(loss=callable)``), class weights, label smoothing, another reduction -- trains on the
+        time-sliced path, which calls ``client.loss_func``."""
+        return _default_ce(c.loss_func) and not (
+            _overrides(c, "local_training") or _overrides(c, "on_train_round_begin")
+            or _overrides(c, "on_train_round_end") or _overrides(c, "set_para")
+            or _overrides(c, "_post_backward") and not hasattr(c, "grad_sign"))
 
     def train_local(self, local_steps: int, lr: float) -> None:
         """Fill U[r] for every local client r."""
@@ -464,6 +474,9 @@ class RoundEngine:
         import os
         if self.device.type != "cuda" or os.environ.get("BLADES_GRAPH", "1") == "0":
             return False
+        return self._stock_types(rows)
+
+    def _stock_types(self, rows: List[int]) -> bool:
         from .. import attackers as A
         stock = (BladesClient, A.NoiseClient, A.LabelflippingClient, A.SignflippingClient, A.AlieClient, A.IpmClient)
         return all(type(self.clients[self.local_idx[r]]) in stock for r in rows)
@@ -754,10 +767,13 @@ class RoundEngine:
         """Graph-replayed time slices for the stock clients among ``rows`` (CUDA).  Returns the rows that
         still need the eager path."""
         import os
-        if self.device.type != "cuda" or os.environ.get("BLADES_GRAPH", "1") == "0" \
-                or self.client_opt_spec not in ("SGD", None, torch.optim.SGD):
+        if self.device.type != "cuda" or self.client_opt_spec not in ("SGD", None, torch.optim.SGD):
             return rows
-        todo = [r for r in rows if self._graph_eligible([r]) and self._stock_for_batching(self.clients[self.local_idx[r]])]
+        # BLADES_GRAPH=0 runs the SAME body eagerly: the result of a run must not depend on the capture policy
+        # (the stock autograd loop computes weight gradients in fp32 cuBLAS, the body with the tf32 tcgen05 kernels)
+        use_graph = os.environ.get("BLADES_GRAPH", "1") != "0"
+        todo = [r for r in rows if self._stock_types([r]) and self._stock_for_batching(self.clients[self.local_idx[r]])
+                ]
         rest = [r for r in rows if r not in set(todo)]
         if not todo:
             return rest
@@ -783,9 +799,26 @@ class RoundEngine:
             X, y = X[0], y[0]
             key = (wi,) + self._sliced_graph_key(c, local_steps, lr, X.shape)
             st = self._sliced_graphs.get(key)
-            if st is None and not self._worth_capturing(self._sliced_graphs, key, lr):
-                self._ragged_data[r] = [(X[j].clone(), y[j].clone()) for j in range(local_steps)]   # eager this time
-                rest.append(r)
+            if st is None and not (use_graph and self._worth_capturing(self._sliced_graphs, key, lr)):
+                # not (yet) captured: the same body, eagerly, on this worker's stream
+                with torch.cuda.stream(stream):
+                    stream.wait_event(ready)
+                    ek = ("eager", wi, tuple(X.shape))
+                    bufs = self._eager_slice_bufs.get(ek)
+                    if bufs is None:
+                        bufs = self._eager_slice_bufs[ek] = (
+                            torch.empty(X.shape, device=self.device, dtype=torch.float32),
+                            torch.empty(y.shape, device=self.device, dtype=torch.int64),
+                            torch.empty(self.d, device=self.device, dtype=torch.float32))
+                    sx, sy, scratch = bufs
+                    sx.copy_(X, non_blocking=True)
+                    sy.copy_(y, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(stream)
+                    self._slice_copied[wi] = ev
+                    self._sliced_body(c, local_steps, lr, sx, sy, scratch, (model_w, flat_w))
+                    self.U[r].copy_(scratch)
+                c._state["saved_update"] = self.U[r]
                 continue
             with torch.cuda.stream(stream):
                 stream.wait_event(ready)

@@ -245,6 +245,11 @@ class Simulator(object):
         eng = self.engine
         agg = self.aggregator
         from .aggregators.base import _BaseAggregator
+        if isinstance(agg, _BaseAggregator) and type(agg).aggregate is _BaseAggregator.aggregate:
+            # reference-style subclass: only ``__call__`` is overridden (it uses ``self._get_updates(inputs)``, e.g.
+            # aggregators/byzantinesgd.py); no server-step fusion, no virtual rows (``_consumes_matrix``)
+            self._last_matrix = None
+            return agg(eng.make_matrix(None))
         if isinstance(agg, _BaseAggregator):
             from .aggregators.fltrust import Fltrust
             matrix = eng.make_matrix(virtual)
@@ -318,8 +323,18 @@ class Simulator(object):
         key = tuple(id(cb) for cb in cbs)
         if getattr(self, "_virt_key", None) != key:
             self._virt_key = key
-            self._virt_val = self.engine.fusable_attack(cbs) if (self._opts["fuse_attack"] and cbs) else None
+            self._virt_val = self.engine.fusable_attack(cbs) if (self._opts["fuse_attack"] and cbs
+                                                                 and self._consumes_matrix()) else None
         return self._virt_val
+
+    def _consumes_matrix(self) -> bool:
+        """Virtual (fused) attack rows exist only inside an ``UpdateMatrix``: they may replace the attacker callbacks
+        only when the aggregator is a built-in style ``_BaseAggregator`` implementing ``aggregate(matrix)``.  A plain
+        callable, or a reference-style subclass that overrides only ``__call__``, sees the clients' real rows, so
+        the callbacks must run for it."""
+        from .aggregators.base import _BaseAggregator
+        agg = self.aggregator
+        return isinstance(agg, _BaseAggregator) and type(agg).aggregate is not _BaseAggregator.aggregate
 
     def _static_round_possible(self, local_steps: int) -> bool:
         """The round is a fixed sequence of device work (no host decisions): fedsgd on the batched engine,

@@ -390,3 +390,57 @@ def test_consecutive_runs_continue_the_data_streams(tmp_path, monkeypatch):
     (b1, b2), sb = go("0")
     assert torch.equal(a1, b1) and torch.equal(a2, b2)
     assert all(sa[k]["pos"] == sb[k]["pos"] and sa[k]["epoch"] == sb[k]["epoch"] for k in sa)
+
+
+# ------------------------------------------------------------------ advisor findings (round 1)
+def _flat(m):
+    return torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+
+
+@pytest.mark.parametrize("attack,akw", [("ipm", {"epsilon": 100.0}), ("alie", {"num_clients": 6, "num_byzantine": 2})])
+def test_custom_callable_aggregator_still_sees_the_fusable_attacks(attack, akw, tmp_log):
+    """ALIE / IPM are normally folded into the aggregation kernel as virtual rows; a plain callable aggregator never
+    sees an UpdateMatrix, so the attacker callbacks must run for it (the defense was evaluated against NO attack)."""
+    def my_mean(clients):
+        return torch.stack([c.get_update() for c in clients]).mean(0)
+    out = []
+    for agg, fuse in ((my_mean, True), ("mean", False)):
+        _, m, _ = _run(agg, attack, 2, None, akw, rounds=2, tmp=tmp_log + str(fuse), fuse_attack=fuse)
+        out.append(_flat(m))
+    assert torch.allclose(out[0], out[1], atol=1e-5), (out[0] - out[1]).abs().max()
+
+
+def test_reference_style_aggregator_subclass_overriding_only_call(tmp_log):
+    """Reference convention (aggregators/mean.py:21-28): subclasses override ``__call__`` and use
+    ``self._get_updates(inputs)``; the shipped ByzantineSGD is one of them."""
+    from blades_b200.aggregators.base import _BaseAggregator
+
+    class RefMean(_BaseAggregator):
+        def __call__(self, inputs):
+            return self._get_updates(inputs).mean(0)
+
+    _, m1, _ = _run(RefMean(), "ipm", 2, None, {"epsilon": 100.0}, tmp=tmp_log + "a")
+    _, m2, _ = _run("mean", "ipm", 2, None, {"epsilon": 100.0}, tmp=tmp_log + "b", fuse_attack=False)
+    assert torch.allclose(_flat(m1), _flat(m2), atol=1e-5)
+
+    from blades_b200.aggregators.byzantinesgd import ByzantineSGD
+    torch.manual_seed(5)
+    model = MLP()
+    opt = torch.optim.SGD(model.parameters(), lr=1.0)
+    agg = ByzantineSGD(6, 1e6, 1e6, 1e6, opt)
+    _, m3, _ = _run(agg, None, 0, tmp=tmp_log + "c", model=model)
+    assert all(torch.isfinite(p).all() for p in m3.parameters())
+
+
+def test_custom_loss_is_honoured_on_the_fedsgd_path(tmp_log):
+    """``run(loss=callable)``: the fused fedsgd pass hard-wires cross-entropy, so such clients train time-sliced."""
+    ds = synthetic_fldataset(4, shape=(28, 28), train_bs=8, seed=3)
+    res = []
+    for steps in (1, 2):
+        sim = Simulator(ds, aggregator="mean", log_path=tmp_log + str(steps), seed=1, progress=False)
+        torch.manual_seed(5)
+        m = MLP()
+        sim.run(m, loss=lambda out, target: out.sum() * 0.0, global_rounds=1, local_steps=steps,
+                validate_interval=10, server_lr=1.0, client_lr=0.1)
+        res.append(sim.last_aggregate.abs().max().item())
+    assert res == [0.0, 0.0], res
