@@ -24,7 +24,25 @@ struct ClientBNParams {
     long long ld;
     int n, B, C, HW;
     float eps, alpha;
+    // fused activation (NHWC kernels only):
+    //   fwd: y = relu?(bn(x) + res)          res optional (residual branch), relu flag
+    //   bwd: g = relu ? gy * (act > 0) : gy  act = the forward OUTPUT; gmask (optional, may alias gy) receives g --
+    //        the gradient the residual branch needs
+    const float* res;
+    const float* act;
+    float* gmask;
+    int relu;
+    int pad_;
 };
+
+__device__ __forceinline__ float4 bn_relu_mask(float4 g, float4 a) {
+    return make_float4(a.x > 0.f ? g.x : 0.f, a.y > 0.f ? g.y : 0.f, a.z > 0.f ? g.z : 0.f, a.w > 0.f ? g.w : 0.f);
+}
+__device__ __forceinline__ float4 bn_act(float4 o, const float4* res, long long idx, int relu) {
+    if (res != nullptr) { const float4 r = res[idx]; o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    return o;
+}
 
 __device__ __forceinline__ float channel_reduce(float v, int HW, float* smem) {
     // sum over the HW threads that own the same channel (HW power of two, segments aligned)
@@ -188,11 +206,12 @@ client_bn_nhwc_fwd_kernel(const __grid_constant__ ClientBNParams p) {
         const float4 g = make_float4(ga.x * rstd.x, ga.y * rstd.y, ga.z * rstd.z, ga.w * rstd.w);
         const float4 sh = make_float4(be.x - mean.x * g.x, be.y - mean.y * g.y, be.z - mean.z * g.z, be.w - mean.w * g.w);
         float4* yb = reinterpret_cast<float4*>(p.y + (long long)c * R * p.C + ch);
+        const float4* rb = p.res ? reinterpret_cast<const float4*>(p.res + (long long)c * R * p.C + ch) : nullptr;
 #pragma unroll 4
         for (int r = rg; r < R; r += kBnGroups) {
             const float4 v = xb[(long long)r * rs];
-            yb[(long long)r * rs] = make_float4(fmaf(v.x, g.x, sh.x), fmaf(v.y, g.y, sh.y), fmaf(v.z, g.z, sh.z),
-                                                fmaf(v.w, g.w, sh.w));
+            yb[(long long)r * rs] = bn_act(make_float4(fmaf(v.x, g.x, sh.x), fmaf(v.y, g.y, sh.y), fmaf(v.z, g.z, sh.z),
+                                                       fmaf(v.w, g.w, sh.w)), rb, (long long)r * rs, p.relu);
         }
         if (rg == 0) {
             *reinterpret_cast<float4*>(p.mean + c * p.C + ch) = mean;
@@ -212,6 +231,8 @@ client_bn_nhwc_bwd_kernel(const __grid_constant__ ClientBNParams p) {
     const long long base = (long long)c * R * p.C + ch;
     const float4* xb = reinterpret_cast<const float4*>(p.x + base);
     const float4* gb = reinterpret_cast<const float4*>(p.gy + base);
+    const float4* ab = reinterpret_cast<const float4*>(p.act + base);       // only dereferenced when p.relu
+    float4* mb = p.gmask ? reinterpret_cast<float4*>(p.gmask + base) : nullptr;
     const long long rs = p.C / 4;
     float4 mean = make_float4(0.f, 0.f, 0.f, 0.f), rstd = mean;
     if (live) {
@@ -222,7 +243,10 @@ client_bn_nhwc_bwd_kernel(const __grid_constant__ ClientBNParams p) {
     if (live) {
 #pragma unroll 4
         for (int r = rg; r < R; r += kBnGroups) {
-            const float4 g = gb[(long long)r * rs], v = xb[(long long)r * rs];
+            float4 g = gb[(long long)r * rs];
+            const float4 v = xb[(long long)r * rs];
+            if (p.relu) g = bn_relu_mask(g, ab[(long long)r * rs]);
+            if (mb != nullptr) mb[(long long)r * rs] = g;
             sb.x += g.x; sb.y += g.y; sb.z += g.z; sb.w += g.w;
             sg.x = fmaf(g.x, (v.x - mean.x) * rstd.x, sg.x);
             sg.y = fmaf(g.y, (v.y - mean.y) * rstd.y, sg.y);
@@ -248,7 +272,9 @@ client_bn_nhwc_bwd_kernel(const __grid_constant__ ClientBNParams p) {
             float4* yb = reinterpret_cast<float4*>(p.y + base);
 #pragma unroll 4
             for (int r = rg; r < R; r += kBnGroups) {
-                const float4 g = gb[(long long)r * rs], v = xb[(long long)r * rs];
+                float4 g = gb[(long long)r * rs];
+                const float4 v = xb[(long long)r * rs];
+                if (p.relu) g = bn_relu_mask(g, ab[(long long)r * rs]);     // idempotent if gmask aliased gy
                 float4 o;
                 o.x = k.x * (g.x - (dbeta.x + (v.x - mean.x) * rstd.x * dgamma.x) * inv_m);
                 o.y = k.y * (g.y - (dbeta.y + (v.y - mean.y) * rstd.y * dgamma.y) * inv_m);
@@ -352,11 +378,12 @@ client_bn_nhwc_fwd_cl_kernel(const __grid_constant__ ClientBNParams p) {
         const float4 g = make_float4(ga.x * rstd.x, ga.y * rstd.y, ga.z * rstd.z, ga.w * rstd.w);
         const float4 sh = make_float4(be.x - mean.x * g.x, be.y - mean.y * g.y, be.z - mean.z * g.z, be.w - mean.w * g.w);
         float4* yb = reinterpret_cast<float4*>(p.y + base);
+        const float4* rb = p.res ? reinterpret_cast<const float4*>(p.res + base) : nullptr;
 #pragma unroll 8
         for (int r = rg; r < Rc; r += GROUPS) {
             const float4 v = bn_tile[r * QUADS + q];
-            yb[(long long)r * rs] = make_float4(fmaf(v.x, g.x, sh.x), fmaf(v.y, g.y, sh.y), fmaf(v.z, g.z, sh.z),
-                                                fmaf(v.w, g.w, sh.w));
+            yb[(long long)r * rs] = bn_act(make_float4(fmaf(v.x, g.x, sh.x), fmaf(v.y, g.y, sh.y), fmaf(v.z, g.z, sh.z),
+                                                       fmaf(v.w, g.w, sh.w)), rb, (long long)r * rs, p.relu);
         }
         if (rg == 0 && rank == 0) {
             *reinterpret_cast<float4*>(p.mean + c * p.C + ch) = mean;
@@ -383,6 +410,8 @@ client_bn_nhwc_bwd_cl_kernel(const __grid_constant__ ClientBNParams p) {
     const long long base = ((long long)c * R + (long long)rank * Rc) * p.C + ch;
     const float4* xb = reinterpret_cast<const float4*>(p.x + base);
     const float4* gb = reinterpret_cast<const float4*>(p.gy + base);
+    const float4* ab = reinterpret_cast<const float4*>(p.act + base);       // only dereferenced when p.relu
+    float4* mb = p.gmask ? reinterpret_cast<float4*>(p.gmask + base) : nullptr;
     float4* xt = bn_tile;
     float4* gt = bn_tile + (size_t)Rc * QUADS;
     const long long rs = p.C / 4;
@@ -395,7 +424,10 @@ client_bn_nhwc_bwd_cl_kernel(const __grid_constant__ ClientBNParams p) {
     if (live) {
 #pragma unroll 4
         for (int r = rg; r < Rc; r += GROUPS) {
-            const float4 g = __ldcs(&gb[(long long)r * rs]), v = __ldcs(&xb[(long long)r * rs]);
+            float4 g = __ldcs(&gb[(long long)r * rs]);
+            const float4 v = __ldcs(&xb[(long long)r * rs]);
+            if (p.relu) g = bn_relu_mask(g, __ldcs(&ab[(long long)r * rs]));
+            if (mb != nullptr) mb[(long long)r * rs] = g;
             const float4 xh = make_float4((v.x - mean.x) * rstd.x, (v.y - mean.y) * rstd.y, (v.z - mean.z) * rstd.z,
                                           (v.w - mean.w) * rstd.w);
             xt[r * QUADS + q] = xh;             // keep xhat, not x

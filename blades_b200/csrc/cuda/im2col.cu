@@ -75,9 +75,10 @@ extern "C" int bl_im2col_rows(const float* x, float* out, int NB, int Cin, int H
 struct Im2colNhwcParams {
     const float* x;
     float* out;
-    int NB, Cin, H, W, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo;
+    int NB, Cin, H, W, kh, kw, sh_, sw_, ph, pw, dh, dw, Ho, Wo;
     long long rows;
     int K, ldk;
+    long long sb, sh, sw, sc;      // element strides of x (NHWC: H*W*C, W*C, C, 1; an NCHW input works too)
 };
 
 template <int VEC>
@@ -93,9 +94,9 @@ im2col_nhwc_kernel(const __grid_constant__ Im2colNhwcParams p) {
             const long long b = row / L;
             const int l = (int)(row - b * L);
             const int ho = l / p.Wo, wo = l - ho * p.Wo;
-            s_base[threadIdx.x] = b * (long long)p.H * p.W * p.Cin;
-            s_h0[threadIdx.x] = ho * p.sh - p.ph;
-            s_w0[threadIdx.x] = wo * p.sw - p.pw;
+            s_base[threadIdx.x] = b * p.sb;
+            s_h0[threadIdx.x] = ho * p.sh_ - p.ph;
+            s_w0[threadIdx.x] = wo * p.sw_ - p.pw;
         } else {
             s_base[threadIdx.x] = -1;
         }
@@ -118,11 +119,11 @@ im2col_nhwc_kernel(const __grid_constant__ Im2colNhwcParams p) {
             float* dst = p.out + (row0 + i) * p.ldk + col;
             if (VEC == 4) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (in) v = __ldg(reinterpret_cast<const float4*>(p.x + base + ((long long)h * p.W + w) * p.Cin + cin));
+                if (in) v = __ldg(reinterpret_cast<const float4*>(p.x + base + h * p.sh + w * p.sw + cin));
                 *reinterpret_cast<float4*>(dst) = v;
             } else {
                 float v = 0.f;
-                if (in) v = __ldg(p.x + base + ((long long)h * p.W + w) * p.Cin + cin);
+                if (in) v = __ldg(p.x + base + h * p.sh + w * p.sw + cin * p.sc);
                 *dst = v;
             }
         }
@@ -130,14 +131,16 @@ im2col_nhwc_kernel(const __grid_constant__ Im2colNhwcParams p) {
 }
 
 extern "C" int bl_im2col_nhwc(const float* x, float* out, int NB, int Cin, int H, int W, int kh, int kw, int sh,
-                              int sw, int ph, int pw, int dh, int dw, int Ho, int Wo, int ldk, void* stream) {
+                              int sw, int ph, int pw, int dh, int dw, int Ho, int Wo, int ldk, long long xsb,
+                              long long xsh, long long xsw, long long xsc, void* stream) {
     Im2colNhwcParams p{x, out, NB, Cin, H, W, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo, (long long)NB * Ho * Wo,
-                       Cin * kh * kw, ldk};
+                       Cin * kh * kw, ldk, xsb, xsh, xsw, xsc};
     if (p.rows <= 0) return 0;
     if (ldk < p.K) return -1;
     const long long blocks = (p.rows + kRowsPerBlock - 1) / kRowsPerBlock;
     if (blocks > 0x7fffffffLL) return -1;
-    const bool vec = (Cin % 4 == 0) && (ldk % 4 == 0) && (((uintptr_t)x) % 16 == 0) && (((uintptr_t)out) % 16 == 0);
+    const bool vec = (Cin % 4 == 0) && (ldk % 4 == 0) && (((uintptr_t)x) % 16 == 0) && (((uintptr_t)out) % 16 == 0) &&
+                     xsc == 1 && xsw % 4 == 0 && xsh % 4 == 0 && xsb % 4 == 0;
     if (vec) im2col_nhwc_kernel<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
     else im2col_nhwc_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
     return (int)cudaGetLastError();

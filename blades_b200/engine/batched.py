@@ -36,7 +36,7 @@ import torch.nn.functional as F
 
 from .flat import ParamSpec
 
-__all__ = ["GradSink", "client_batched", "is_batchable", "batched_loss", "BatchedUnsupported"]
+__all__ = ["GradSink", "client_batched", "is_batchable", "batched_loss", "batched_step", "BatchedUnsupported"]
 
 
 class BatchedUnsupported(RuntimeError):
@@ -384,3 +384,18 @@ def batched_loss(logits: torch.Tensor, target: torch.Tensor, n: int, clamp: torc
     per_client = per_sample.view(n, -1).mean(1)
     clamped = torch.minimum(per_client.clamp_min(0), clamp)
     return clamped.sum(), per_client.detach()
+
+
+def batched_step(model: nn.Module, sink: GradSink, x: torch.Tensor, y: torch.Tensor, n: int,
+                 clamp: torch.Tensor) -> torch.Tensor:
+    """One client-batched fedsgd step: fills ``sink`` with ``alpha * grad_c`` for the ``n`` clients whose samples are
+    concatenated in ``x`` / ``y`` and returns the per-client mean losses.  The ResNet family runs the explicit
+    all-own-kernels schedule (``engine/resnet_fused.py``) on B200; everything else the swapped-forward autograd pass."""
+    from . import resnet_fused as rf
+    if rf.supports(model, sink, x):
+        return rf.step(model, sink, x, y, n, clamp)
+    with client_batched(model, sink, x.shape[0]):
+        logits = model(x)
+        loss, per_client = batched_loss(logits, y, n, clamp)
+        loss.backward()
+    return per_client

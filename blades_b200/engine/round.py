@@ -686,10 +686,7 @@ class RoundEngine:
         out = self.U[rows[0]: rows[0] + n] if contiguous_rows else torch.empty(n, self.d, device=self.device)
         sink = cb.GradSink(out, self.gflat.specs, n, alpha=-lr)
         model.train()
-        with cb.client_batched(model, sink, n * B):
-            logits = model(X.reshape((n * B,) + tuple(X.shape[2:])))
-            loss, per_client = cb.batched_loss(logits, y.reshape(-1), n, clamp)
-            loss.backward()
+        per_client = cb.batched_step(model, sink, X.reshape((n * B,) + tuple(X.shape[2:])), y.reshape(-1), n, clamp)
         missing = [s.name for s in self.gflat.specs if s.name not in sink.written]
         for name in missing:       # parameters unused in the forward pass: zero update
             sink.view(name).zero_()

@@ -13,7 +13,8 @@ class ClientBNParams(C.Structure):
     _fields_ = [("x", C.c_void_p), ("gy", C.c_void_p), ("y", C.c_void_p), ("gamma", C.c_void_p),
                 ("beta", C.c_void_p), ("mean", C.c_void_p), ("rstd", C.c_void_p), ("dgamma", C.c_void_p),
                 ("dbeta", C.c_void_p), ("ld", C.c_longlong), ("n", C.c_int), ("B", C.c_int), ("C", C.c_int),
-                ("HW", C.c_int), ("eps", C.c_float), ("alpha", C.c_float)]
+                ("HW", C.c_int), ("eps", C.c_float), ("alpha", C.c_float),
+                ("res", C.c_void_p), ("act", C.c_void_p), ("gmask", C.c_void_p), ("relu", C.c_int), ("pad_", C.c_int)]
 
 
 _checked = False
@@ -32,6 +33,13 @@ def is_nhwc(x: torch.Tensor) -> bool:
             and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous())
 
 
+def _same_layout(a: torch.Tensor, x: torch.Tensor) -> bool:
+    """Same shape and both NHWC-dense (strides of size-1 dimensions are arbitrary in torch, so compare contiguity)."""
+    cl = torch.channels_last
+    return a.shape == x.shape and a.dtype == x.dtype and a.is_contiguous(memory_format=cl) \
+        and x.is_contiguous(memory_format=cl)
+
+
 def _lib():
     global _checked
     lib = _loader.cuda_lib()
@@ -41,10 +49,13 @@ def _lib():
     return lib
 
 
-def forward(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, n: int, eps: float
+def forward(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, n: int, eps: float,
+            res: Optional[torch.Tensor] = None, relu: bool = False, nhwc: Optional[bool] = None
             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """``y = relu?(bn_per_client(x) + res)``; the fused residual / ReLU exist in the NHWC kernels only."""
     NB, Cc, H, W = x.shape
-    nhwc = is_nhwc(x)
+    nhwc = is_nhwc(x) if nhwc is None else nhwc
+    assert nhwc or (res is None and not relu)
     if nhwc:                                # float4 parameter loads need 16 B alignment
         gamma = gamma if gamma.data_ptr() % 16 == 0 else gamma.clone()
         beta = beta if beta.data_ptr() % 16 == 0 else beta.clone()
@@ -53,6 +64,10 @@ def forward(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, n: int, ep
     rstd = torch.empty(n, Cc, device=x.device, dtype=torch.float32)
     p = ClientBNParams(x.data_ptr(), None, y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(),
                        rstd.data_ptr(), None, None, 0, n, NB // n, Cc, H * W, float(eps), 1.0)
+    if res is not None:
+        assert _same_layout(res, x)
+        p.res = res.data_ptr()
+    p.relu = 1 if relu else 0
     fn = _lib().bl_client_bn_nhwc_fwd if nhwc else _lib().bl_client_bn_fwd
     _loader.check(fn(C.byref(p), _loader.stream_ptr(x.device)), "client_bn_fwd")
     _loader.count_launch()
@@ -60,11 +75,15 @@ def forward(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, n: int, ep
 
 
 def backward(gy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor,
-             n: int, dgamma_view: torch.Tensor, dbeta_view: torch.Tensor, alpha: float, need_dx: bool
+             n: int, dgamma_view: torch.Tensor, dbeta_view: torch.Tensor, alpha: float, need_dx: bool,
+             act: Optional[torch.Tensor] = None, gmask: Optional[torch.Tensor] = None, nhwc: Optional[bool] = None
              ) -> Optional[torch.Tensor]:
-    """``dgamma_view`` / ``dbeta_view``: strided ``[n, C]`` windows of the update matrix (row stride ld)."""
+    """``dgamma_view`` / ``dbeta_view``: strided ``[n, C]`` windows of the update matrix (row stride ld).
+    ``act`` (NHWC only): the forward OUTPUT of a fused ReLU -- the incoming gradient is masked with ``act > 0``
+    first; ``gmask`` (may be ``gy`` itself) receives that masked gradient (what a residual branch needs)."""
     NB, Cc, H, W = x.shape
-    nhwc = is_nhwc(x)
+    nhwc = is_nhwc(x) if nhwc is None else nhwc
+    assert nhwc or (act is None and gmask is None)
     if nhwc and gamma.data_ptr() % 16:
         gamma = gamma.clone()
     gy = gy.contiguous(memory_format=torch.channels_last) if nhwc else gy.contiguous()
@@ -73,6 +92,12 @@ def backward(gy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.
     p = ClientBNParams(x.data_ptr(), gy.data_ptr(), dx.data_ptr() if need_dx else None, gamma.data_ptr(), None,
                        mean.data_ptr(), rstd.data_ptr(), dgamma_view.data_ptr(), dbeta_view.data_ptr(),
                        dgamma_view.stride(0), n, NB // n, Cc, H * W, 0.0, float(alpha))
+    if act is not None:
+        assert _same_layout(act, x)
+        p.act, p.relu = act.data_ptr(), 1
+    if gmask is not None:
+        assert _same_layout(gmask, x)
+        p.gmask = gmask.data_ptr()
     fn = _lib().bl_client_bn_nhwc_bwd if nhwc else _lib().bl_client_bn_bwd
     _loader.check(fn(C.byref(p), _loader.stream_ptr(x.device)), "client_bn_bwd")
     _loader.count_launch()

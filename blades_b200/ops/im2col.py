@@ -40,15 +40,15 @@ def im2col_nhwc(x: torch.Tensor, kernel, stride, padding, dilation, out_hw) -> t
     if not x.is_cuda or x.dtype != torch.float32:
         cols = F.unfold(x, kernel, dilation=dilation, padding=padding, stride=stride)      # [NB, Cin*kh*kw, L]
         return cols.view(NB, Cin, kh * kw, Ho * Wo).permute(0, 3, 2, 1).reshape(NB * Ho * Wo, K)
-    xp = x.permute(0, 2, 3, 1)
-    if not xp.is_contiguous():
-        xp = xp.contiguous()
     ldk = (K + 3) // 4 * 4
     out = torch.empty(NB * Ho * Wo, ldk, device=x.device, dtype=torch.float32)
     lib = _loader.cuda_lib()
-    lib.bl_im2col_nhwc.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 15 + [C.c_void_p]
-    _loader.check(lib.bl_im2col_nhwc(xp.data_ptr(), out.data_ptr(), NB, Cin, H, W, kh, kw, stride[0], stride[1],
+    lib.bl_im2col_nhwc.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 15 + [C.c_longlong] * 4 + [C.c_void_p]
+    # any strided [NB, Cin, H, W] input: a channels_last tensor moves float4 channel runs, an NCHW one (the network
+    # input) is read element-wise -- no layout conversion pass either way
+    _loader.check(lib.bl_im2col_nhwc(x.data_ptr(), out.data_ptr(), NB, Cin, H, W, kh, kw, stride[0], stride[1],
                                      padding[0], padding[1], dilation[0], dilation[1], Ho, Wo, ldk,
+                                     x.stride(0), x.stride(2), x.stride(3), x.stride(1),
                                      _loader.stream_ptr(x.device)), "im2col_nhwc")
     _loader.count_launch()
     return out[:, :K]

@@ -210,10 +210,8 @@ def _batched_rows_gpu(model, X, y, lr):
     U = torch.zeros(n, ld, device=X.device)[:, :flat.numel]
     sink = cb.GradSink(U, flat.specs, n, alpha=-lr)
     model.train()
-    with cb.client_batched(model, sink, n * B):
-        logits = model(X.reshape((n * B,) + tuple(X.shape[2:])))
-        loss, _ = cb.batched_loss(logits, y.reshape(-1), n, torch.full((n,), 1e6, device=X.device))
-        loss.backward()
+    cb.batched_step(model, sink, X.reshape((n * B,) + tuple(X.shape[2:])), y.reshape(-1), n,
+                    torch.full((n,), 1e6, device=X.device))
     return U, flat
 
 

@@ -47,7 +47,7 @@ def test_library_targets_sm_100a_only():
     assert archs == {"100a"}, archs
 
 
-@pytest.mark.parametrize("kernel", ["gram_tcgen05_kernel", "wgrad_tcgen05_kernel"])
+@pytest.mark.parametrize("kernel", ["gram_tcgen05_kernel", "wgrad_tcgen05_kernel", "conv_tcgen05_kernel"])
 def test_tensor_core_kernels_use_tcgen05_tmem_and_tma(sass, kernel):
     for k in _find(sass, kernel):
         ops = sass[k]
