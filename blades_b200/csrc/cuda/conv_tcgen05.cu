@@ -116,7 +116,10 @@ conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
         // ================= TMA producer =================
         if (lane == 0) {
             const uint32_t tx = (uint32_t)p.rows * 128u + b_bytes;
-            uint32_t it = 0;
+            // running stage / parity: no integer divisions in the single-thread issue loops (ncu: with `it % stages`
+            // the producer iteration, not L2 or the tensor pipe, paced the whole kernel)
+            int s = 0;
+            uint32_t par = 0;
             for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m = (int)(tile % m_tiles);
                 const long long rest = tile / m_tiles;
@@ -126,9 +129,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
                 for (int t = 0; t < ph.ntaps; ++t) {
                     const int xw = ph.dx[t], xh = h0 * p.cs + ph.dy[t];
                     const int wcol = (int)ph.widx[t] * p.wtap_stride;
-                    for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
-                        const int s = it % p.stages;
-                        const uint32_t par = (it / p.stages) & 1u;
+                    for (int cb = 0; cb < p.cblocks; ++cb) {
                         bl::mbar_wait(&empty[s], par ^ 1u);
                         bl::mbar_arrive_expect_tx(&full[s], tx);
                         uint8_t* dst = tiles + (size_t)s * stage_bytes;
@@ -140,6 +141,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
                                 bl::tma_load_2d(dst + kABytes + j * 4096, &p.map_b, &full[s],
                                                 wcol + nt * p.BN + j * 32, cb * 32);
                         }
+                        if (++s == p.stages) { s = 0; par ^= 1u; }
                     }
                 }
             }
@@ -147,7 +149,15 @@ conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
     } else if (warp == 1) {
         // ================= MMA issuer =================
         const uint32_t idesc = bl::umma_idesc_tf32(128, (uint32_t)p.BN, 0, (uint32_t)p.b_mn_major);
-        uint32_t it = 0, tcount = 0;
+        uint32_t tcount = 0;
+        int s = 0;
+        uint32_t par = 0;
+        const uint32_t tiles0 = bl::smem_u32(tiles);
+        // descriptors of stage 0 / K atom 0; the start-address field (bits 0-13, address >> 4) advances by plain adds
+        const uint64_t ad0 = bl::umma_smem_desc(tiles0, 16, 1024, bl::kLayoutSw128);
+        const uint64_t bd0 = p.b_mn_major ? bl::umma_smem_desc(tiles0 + kABytes, 4096, 512, bl::kLayoutSw128Base32B)
+                                          : bl::umma_smem_desc(tiles0 + kABytes, 16, 1024, bl::kLayoutSw128);
+        const uint32_t bk = p.b_mn_major ? (1024u >> 4) : (32u >> 4);
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const ConvPhase& ph = p.ph[(int)((tile / m_tiles) / p.n_tiles)];
             const int ksteps = ph.ntaps * p.cblocks;
@@ -158,26 +168,20 @@ conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
             bl::mbar_wait(&tempty[buf], tph ^ 1u);
             bl::tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * 256u;
-            for (int ks = 0; ks < ksteps; ++ks, ++it) {
-                const int s = it % p.stages;
-                const uint32_t par = (it / p.stages) & 1u;
+            for (int ks = 0; ks < ksteps; ++ks) {
                 bl::mbar_wait(&full[s], par);
                 bl::tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t a0 = bl::smem_u32(tiles + (size_t)s * stage_bytes);
-                    const uint32_t b0 = a0 + kABytes;
+                    const uint64_t so = (uint64_t)(((uint32_t)s * stage_bytes) >> 4);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {           // K = 8 tf32 (32 B of the 128 B row) per MMA
-                        const uint64_t ad = bl::umma_smem_desc(a0 + k * 32u, 16, 1024, bl::kLayoutSw128);
-                        const uint64_t bd = p.b_mn_major
-                            ? bl::umma_smem_desc(b0 + k * 1024u, 4096, 512, bl::kLayoutSw128Base32B)
-                            : bl::umma_smem_desc(b0 + k * 32u, 16, 1024, bl::kLayoutSw128);
-                        bl::umma_tf32(d_tmem, ad, bd, idesc, (ks > 0 || k > 0) ? 1u : 0u);
-                    }
+                    for (int k = 0; k < 4; ++k)             // K = 8 tf32 (32 B of the 128 B row) per MMA
+                        bl::umma_tf32(d_tmem, ad0 + so + (uint64_t)(k * 2), bd0 + so + (uint64_t)(k * bk), idesc,
+                                      (ks > 0 || k > 0) ? 1u : 0u);
                     bl::umma_commit(&empty[s]);
                     if (ks == ksteps - 1) bl::umma_commit(&tfull[buf]);
                 }
                 __syncwarp();
+                if (++s == p.stages) { s = 0; par ^= 1u; }
             }
         }
     } else {

@@ -120,9 +120,9 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
             // ================= TMA producer =================
             if (lane == 0) {
                 const uint32_t tx = (uint32_t)p.rows_covered * rb * (uint32_t)p.slabs;
-                for (int it = 0; it < iters; ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                int s = 0;
+                uint32_t ph = 0;
+                for (int it = 0; it < iters; ++it, s = (s + 1 == p.stages) ? 0 : s + 1, ph ^= (s == 0) ? 1u : 0u) {
                     bl::mbar_wait(&empty[s], ph ^ 1u);
                     bl::mbar_arrive_expect_tx(&full[s], tx);
                     uint8_t* dst = tiles + (size_t)s * stage_bytes;
@@ -137,9 +137,9 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
         } else if (warp == 1) {
             // ================= MMA issuer =================
             const int n_halves = (p.np_n + 255) / 256;
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int it = 0; it < iters; ++it, s = (s + 1 == p.stages) ? 0 : s + 1, ph ^= (s == 0) ? 1u : 0u) {
                 bl::mbar_wait(&ready[s], ph);
                 bl::tc_fence_after();
                 if (lane == 0) {
@@ -180,9 +180,9 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
             // ================= converter (warps 2..5) =================
             const int ct = threadIdx.x - 64;                       // 0..255
             const uint32_t n16 = (uint32_t)p.rows_covered * (rb / 16u);   // 16 B granules in the covered part of a slab
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int it = 0; it < iters; ++it, s = (s + 1 == p.stages) ? 0 : s + 1, ph ^= (s == 0) ? 1u : 0u) {
                 bl::mbar_wait(&full[s], ph);
                 for (int sl = 0; sl < ((p.dbg & 1) ? 0 : p.slabs); ++sl) {
                 uint8_t* hi = tiles + (size_t)s * stage_bytes + (size_t)sl * slab_bytes;

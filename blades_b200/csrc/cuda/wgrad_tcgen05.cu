@@ -81,14 +81,15 @@ wgrad_tcgen05_kernel(const __grid_constant__ WgradParams p) {
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            uint32_t it = 0;
+            int s = 0;                      // running stage / parity: no integer divisions in the issue loops
+            uint32_t ph = 0;
+            const int hchunks = p.implicit ? p.Ho / p.bh : 1;
             for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int nt = (int)(tile % p.n_tiles);
                 const int mt = (int)((tile / p.n_tiles) % p.m_tiles);
                 const int c = (int)(tile / ((long long)p.n_tiles * p.m_tiles));
-                for (int ks = 0; ks < ksteps; ++ks, ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (it / p.stages) & 1u;
+                int kb = 0, kh = 0;         // implicit mode: sample-group / row-chunk counters of the K step
+                for (int ks = 0; ks < ksteps; ++ks) {
                     bl::mbar_wait(&empty[s], ph ^ 1u);
                     bl::mbar_arrive_expect_tx(&full[s], stage_bytes);
                     uint8_t* dst = tiles + (size_t)s * stage_bytes;
@@ -104,51 +105,55 @@ wgrad_tcgen05_kernel(const __grid_constant__ WgradParams p) {
                         // K chunk ks = output positions (b0..b0+bb) x (ho0..ho0+bh) x (0..Wo) of client c; for the
                         // 32-channel block (tap, cin0) the matching input pixels are one strided 4-D TMA box; conv
                         // padding = out-of-range coordinates, zero-filled by TMA.
-                        const int hchunks = p.Ho / p.bh;
-                        const int b0 = (ks / hchunks) * p.bb, ho0 = (ks % hchunks) * p.bh;
+                        const int b0 = kb * p.bb, ho0 = kh * p.bh;
+                        int n0 = nt * p.BN;
+                        int tap = n0 / p.Cin, cin0 = n0 - tap * p.Cin;          // one division per K step, then running
+                        int r = tap / p.kw, sx = tap - r * p.kw;
                         for (uint32_t j = 0; j < nb_blocks; ++j) {
-                            const int n0 = nt * p.BN + (int)j * 32;
-                            const int tap = n0 / p.Cin, cin0 = n0 - tap * p.Cin;
-                            const int r = tap / p.kw, sx = tap - r * p.kw;
                             const bool valid = tap < p.taps;
                             bl::tma_load_4d(dst + a_bytes + j * box_bytes, &p.map_x, &full[s],
                                             valid ? cin0 : p.Cin,           // beyond the channel extent -> zeros
                                             sx - p.cp, ho0 * p.cs + r - p.cp, c * p.Bc + b0);
+                            cin0 += 32;
+                            if (cin0 >= p.Cin) { cin0 = 0; ++tap; if (++sx == p.kw) { sx = 0; ++r; } }
                         }
+                        if (++kh == hchunks) { kh = 0; ++kb; }
                     }
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         const uint32_t idesc = bl::umma_idesc_tf32(128, (uint32_t)p.BN, 1, 1);
-        uint32_t it = 0, tcount = 0;
+        uint32_t tcount = 0;
+        int s = 0;
+        uint32_t ph = 0;
+        const uint32_t tiles0 = bl::smem_u32(tiles);
+        const uint64_t ad0 = bl::umma_smem_desc(tiles0, box_bytes, 512u, bl::kLayoutSw128Base32B);
+        const uint64_t bd0 = bl::umma_smem_desc(tiles0 + a_bytes, box_bytes, 512u, bl::kLayoutSw128Base32B);
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
             const uint32_t buf = tcount & 1u;
             const uint32_t tph = (tcount >> 1) & 1u;
             bl::mbar_wait(&tempty[buf], tph ^ 1u);             // epilogue drained this accumulator
             bl::tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * 256u;
-            for (int ks = 0; ks < ksteps; ++ks, ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (it / p.stages) & 1u;
+            for (int ks = 0; ks < ksteps; ++ks) {
                 bl::mbar_wait(&full[s], ph);
                 bl::tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t a0 = bl::smem_u32(tiles + (size_t)s * stage_bytes);
-                    const uint32_t b0 = a0 + a_bytes;
-                    for (int ka = 0; ka < p.KT / 8; ++ka) {    // one 8-row K atom (1024 B) per MMA
-                        // MN-major tf32: SWIZZLE_128B_BASE32B; LBO = stride between 32-float column
-                        // blocks, SBO = stride between 4-row K atoms (rows are contiguous: 512 B)
-                        const uint32_t lbo = box_bytes, sbo = 512u;
-                        const uint64_t ad = bl::umma_smem_desc(a0 + ka * 1024u, lbo, sbo, bl::kLayoutSw128Base32B);
-                        const uint64_t bd = bl::umma_smem_desc(b0 + ka * 1024u, lbo, sbo, bl::kLayoutSw128Base32B);
-                        bl::umma_tf32(d_tmem, ad, bd, idesc, (ks > 0 || ka > 0) ? 1u : 0u);
-                    }
+                    // MN-major tf32: SWIZZLE_128B_BASE32B; LBO = stride between 32-float column blocks, SBO = stride
+                    // between 4-row K atoms (rows are contiguous: 512 B); one 8-row K atom (1024 B) per MMA.  The
+                    // start-address field of the descriptors (address >> 4) advances by plain adds.
+                    const uint64_t so = (uint64_t)(((uint32_t)s * stage_bytes) >> 4);
+                    for (int ka = 0; ka < p.KT / 8; ++ka)
+                        bl::umma_tf32(d_tmem, ad0 + so + (uint64_t)(ka * 64), bd0 + so + (uint64_t)(ka * 64), idesc,
+                                      (ks > 0 || ka > 0) ? 1u : 0u);
                     bl::umma_commit(&empty[s]);
                     if (ks == ksteps - 1) bl::umma_commit(&tfull[buf]);
                 }
                 __syncwarp();
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else {

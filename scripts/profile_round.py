@@ -31,7 +31,7 @@ print(f"GPU kernel time per round: {tot / R / 1e3:.3f} ms over {sum(e.count for 
 for e in ev[:40]:
     print(f"{e.device_time_total / R / 1e3:8.3f} ms  {e.count // R:5d}x  {e.key[:130]}")
 # per-launch durations of our kernels in launch order (last profiled round)
-mine = [e for e in prof.events() if e.device_time_total > 0 and any(k in e.name for k in ("wgrad_tcgen05", "client_bn", "im2col", "coord_select"))]
+mine = [e for e in prof.events() if e.device_time_total > 0 and any(k in e.name for k in ("tcgen05", "client_", "im2col", "coord_select", "pool", "pad_rows"))]
 mine.sort(key=lambda e: e.time_range.start)
 per = len(mine) // R
 print("--- per-launch (one round, launch order = backward order of the layers) ---")
