@@ -73,6 +73,8 @@ struct ConvParams {
     const float* add;
     const float* bias;
     int accumulate_only, stages, vec_ok;
+    int kpack;               // 32-channel K blocks per pipeline stage (fewer barrier round trips per byte)
+    int dbg;                 // timing bisect (BLADES_CONV_DBG): 1 no B loads, 2 no A loads, 4 no MMAs, 8 no stores
     ConvPhase ph[CONV_MAX_PHASES];
 };
 
@@ -85,7 +87,8 @@ __global__ void __launch_bounds__(kCThreads, 1)
 conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t b_bytes = (uint32_t)p.BN * 128u;
-    const uint32_t stage_bytes = kABytes + b_bytes;
+    const uint32_t a_stage = kABytes * (uint32_t)p.kpack;
+    const uint32_t stage_bytes = a_stage + b_bytes * (uint32_t)p.kpack;
     uint8_t* tiles = smem_raw;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)p.stages * stage_bytes);
     uint64_t* full = bars;
@@ -95,7 +98,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
     float* epi = reinterpret_cast<float*>(tiles + (size_t)p.stages * stage_bytes + 256);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = bl::uniform_warp_idx(), lane = threadIdx.x & 31;
     const int m_tiles = p.h_tiles * p.b_tiles;
     const long long total_tiles = (long long)p.n_phases * p.n_tiles * m_tiles;
 
@@ -111,38 +114,45 @@ conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
     __syncthreads();
     bl::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tiles0 = bl::smem_u32(tiles);
+    const uint32_t full0 = bl::smem_u32(full), empty0 = bl::smem_u32(empty);
+    const uint32_t tfull0 = bl::smem_u32(tfull), tempty0 = bl::smem_u32(tempty);
 
+    // Warps 0 and 1 run their loops CONVERGED (all 32 lanes, uniform values, election inside the asm statements): see
+    // tc_common.cuh "warp-uniform issue".  Stage / parity are running counters (no integer divisions).
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
-            const uint32_t tx = (uint32_t)p.rows * 128u + b_bytes;
-            // running stage / parity: no integer divisions in the single-thread issue loops (ncu: with `it % stages`
-            // the producer iteration, not L2 or the tensor pipe, paced the whole kernel)
-            int s = 0;
-            uint32_t par = 0;
-            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m = (int)(tile % m_tiles);
-                const long long rest = tile / m_tiles;
-                const int nt = (int)(rest % p.n_tiles);
-                const ConvPhase& ph = p.ph[(int)(rest / p.n_tiles)];
-                const int h0 = (m % p.h_tiles) * p.bh, b0 = (m / p.h_tiles) * p.bb;
-                for (int t = 0; t < ph.ntaps; ++t) {
-                    const int xw = ph.dx[t], xh = h0 * p.cs + ph.dy[t];
-                    const int wcol = (int)ph.widx[t] * p.wtap_stride;
-                    for (int cb = 0; cb < p.cblocks; ++cb) {
-                        bl::mbar_wait(&empty[s], par ^ 1u);
-                        bl::mbar_arrive_expect_tx(&full[s], tx);
-                        uint8_t* dst = tiles + (size_t)s * stage_bytes;
-                        bl::tma_load_4d(dst, &p.map_a, &full[s], cb * 32, xw, xh, b0);
-                        if (!p.b_mn_major) {
-                            bl::tma_load_2d(dst + kABytes, &p.map_b, &full[s], wcol + cb * 32, nt * p.BN);
+        const uint32_t tx = (((p.dbg & 2) ? 0u : (uint32_t)p.rows * 128u) + ((p.dbg & 1) ? 0u : b_bytes)) *
+                            (uint32_t)p.kpack;
+        int s = 0;
+        uint32_t par = 0;
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m = (int)(tile % m_tiles);
+            const long long rest = tile / m_tiles;
+            const int nt = (int)(rest % p.n_tiles);
+            const ConvPhase& ph = p.ph[(int)(rest / p.n_tiles)];
+            const int h0 = (m % p.h_tiles) * p.bh, b0 = (m / p.h_tiles) * p.bb;
+            for (int t = 0; t < ph.ntaps; ++t) {
+                const int xw = ph.dx[t], xh = h0 * p.cs + ph.dy[t];
+                const int wcol = (int)ph.widx[t] * p.wtap_stride;
+                for (int cb = 0; cb < p.cblocks; cb += p.kpack) {
+                    bl::mbar_wait_u32(empty0 + 8u * s, par ^ 1u);
+                    const uint32_t fb = full0 + 8u * s;
+                    bl::mbar_arrive_expect_tx_e(fb, tx);
+                    const uint32_t dst = tiles0 + (uint32_t)s * stage_bytes;
+                    for (int kp = 0; kp < p.kpack; ++kp) {
+                        const int c0 = (cb + kp) * 32;
+                        if (!(p.dbg & 2)) bl::tma_load_4d_e(dst + kp * kABytes, &p.map_a, fb, c0, xw, xh, b0);
+                        const uint32_t db = dst + a_stage + kp * b_bytes;
+                        if (p.dbg & 1) {
+                        } else if (!p.b_mn_major) {
+                            bl::tma_load_2d_e(db, &p.map_b, fb, wcol + c0, nt * p.BN);
                         } else {
                             for (int j = 0; j < p.BN / 32; ++j)
-                                bl::tma_load_2d(dst + kABytes + j * 4096, &p.map_b, &full[s],
-                                                wcol + nt * p.BN + j * 32, cb * 32);
+                                bl::tma_load_2d_e(db + j * 4096, &p.map_b, fb, wcol + nt * p.BN + j * 32, c0);
                         }
-                        if (++s == p.stages) { s = 0; par ^= 1u; }
                     }
+                    if (++s == p.stages) { s = 0; par ^= 1u; }
                 }
             }
         }
@@ -152,35 +162,36 @@ conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
         uint32_t tcount = 0;
         int s = 0;
         uint32_t par = 0;
-        const uint32_t tiles0 = bl::smem_u32(tiles);
         // descriptors of stage 0 / K atom 0; the start-address field (bits 0-13, address >> 4) advances by plain adds
         const uint64_t ad0 = bl::umma_smem_desc(tiles0, 16, 1024, bl::kLayoutSw128);
-        const uint64_t bd0 = p.b_mn_major ? bl::umma_smem_desc(tiles0 + kABytes, 4096, 512, bl::kLayoutSw128Base32B)
-                                          : bl::umma_smem_desc(tiles0 + kABytes, 16, 1024, bl::kLayoutSw128);
+        const uint64_t bd0 = p.b_mn_major ? bl::umma_smem_desc(tiles0 + a_stage, 4096, 512, bl::kLayoutSw128Base32B)
+                                          : bl::umma_smem_desc(tiles0 + a_stage, 16, 1024, bl::kLayoutSw128);
         const uint32_t bk = p.b_mn_major ? (1024u >> 4) : (32u >> 4);
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const ConvPhase& ph = p.ph[(int)((tile / m_tiles) / p.n_tiles)];
-            const int ksteps = ph.ntaps * p.cblocks;
+            const int ksteps = ph.ntaps * (p.cblocks / p.kpack);
             if (ksteps == 0) continue;
             const uint32_t buf = tcount & 1u;
             const uint32_t tph = (tcount >> 1) & 1u;
             ++tcount;
-            bl::mbar_wait(&tempty[buf], tph ^ 1u);
+            bl::mbar_wait_u32(tempty0 + 8u * buf, tph ^ 1u);
             bl::tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * 256u;
             for (int ks = 0; ks < ksteps; ++ks) {
-                bl::mbar_wait(&full[s], par);
+                bl::mbar_wait_u32(full0 + 8u * s, par);
                 bl::tc_fence_after();
-                if (lane == 0) {
-                    const uint64_t so = (uint64_t)(((uint32_t)s * stage_bytes) >> 4);
+                const uint64_t so = (uint64_t)(((uint32_t)s * stage_bytes) >> 4);
+                for (int kp = 0; kp < p.kpack; ++kp) {
+                    const uint64_t ao = so + (uint64_t)((kp * kABytes) >> 4), bo = so + (uint64_t)((kp * b_bytes) >> 4);
+                    if (!(p.dbg & 4)) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)             // K = 8 tf32 (32 B of the 128 B row) per MMA
-                        bl::umma_tf32(d_tmem, ad0 + so + (uint64_t)(k * 2), bd0 + so + (uint64_t)(k * bk), idesc,
-                                      (ks > 0 || k > 0) ? 1u : 0u);
-                    bl::umma_commit(&empty[s]);
-                    if (ks == ksteps - 1) bl::umma_commit(&tfull[buf]);
+                        for (int k = 0; k < 4; ++k)         // K = 8 tf32 (32 B of the 128 B row) per MMA
+                            bl::umma_tf32_e(d_tmem, ad0 + ao + (uint64_t)(k * 2), bd0 + bo + (uint64_t)(k * bk), idesc,
+                                            (ks > 0 || kp > 0 || k > 0) ? 1u : 0u);
+                    }
                 }
-                __syncwarp();
+                bl::umma_commit_e(empty0 + 8u * s);
+                if (ks == ksteps - 1) bl::umma_commit_e(tfull0 + 8u * buf);
                 if (++s == p.stages) { s = 0; par ^= 1u; }
             }
         }
@@ -246,7 +257,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
                     const int r = i * 4 + rsub;
                     float4 t = *reinterpret_cast<const float4*>(stg + r * kCEpiLd + csub);
                     t.x += bs.x; t.y += bs.y; t.z += bs.z; t.w += bs.w;
-                    if ((okmask >> i) & 1u) {
+                    if (((okmask >> i) & 1u) && !(p.dbg & 8)) {
                         const long long o = off[i] + n0 + csub;
                         if (p.vec_ok && n0 + csub + 4 <= p.N) {
                             if (p.add != nullptr) {
@@ -333,6 +344,7 @@ extern "C" int bl_conv_tc(const ConvDesc* d, void* stream) {
     p.vec_ok = (((uintptr_t)d->out) % 16 == 0) && (d->ldc % 4 == 0) &&
                (d->add == nullptr || ((uintptr_t)d->add) % 16 == 0);
     memcpy(p.ph, d->ph, sizeof(p.ph));
+    { const char* e = getenv("BLADES_CONV_DBG"); p.dbg = e ? atoi(e) : 0; }
     {
         uint64_t dims[4] = {(uint64_t)d->Cs, (uint64_t)d->Ws, (uint64_t)d->Hs, (uint64_t)d->NB};
         uint64_t strides[3] = {(uint64_t)d->lds * 4, (uint64_t)d->Ws * d->lds * 4, (uint64_t)d->Hs * d->Ws * d->lds * 4};
@@ -349,9 +361,20 @@ extern "C" int bl_conv_tc(const ConvDesc* d, void* stream) {
                                   p.b_mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
         if (r != 0) return 2000 + r;
     }
-    const size_t stage_bytes = kABytes + (size_t)bn * 128;
     const size_t epi_bytes = 8 * 32 * kCEpiLd * sizeof(float);
-    int stages = (int)((227 * 1024 - 1024 - 256 - epi_bytes) / stage_bytes);
+    const size_t budget = 227 * 1024 - 1024 - 256 - epi_bytes;
+    int kpack = 1;
+    {
+        const char* e = getenv("BLADES_CONV_KPACK");
+        const int want = e ? atoi(e) : 2;
+        // K blocks per stage: as many as leave a 4-deep pipeline (measured: 64-channel layers 64 -> 58 us with 2 blocks
+        // per stage; a 3-deep pipeline of 64 KB stages halves the speed of the stride-2 gathers)
+        for (int kp = 4; kp >= 2; kp /= 2)
+            if (kp <= want && p.cblocks % kp == 0 && budget / ((kABytes + (size_t)bn * 128) * kp) >= 4) { kpack = kp; break; }
+    }
+    p.kpack = kpack;
+    const size_t stage_bytes = (kABytes + (size_t)bn * 128) * kpack;
+    int stages = (int)(budget / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) return -2;
     p.stages = stages;

@@ -69,7 +69,7 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
     uint64_t* done = bars + 3 * p.stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 1);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = bl::uniform_warp_idx();      // warp-uniform role index (tc_common.cuh "warp-uniform issue")
     const int lane = threadIdx.x & 31;
 
     // ---- work assignment
@@ -117,34 +117,40 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
 
     if (iters > 0) {
         if (warp == 0) {
-            // ================= TMA producer =================
-            if (lane == 0) {
+            // ================= TMA producer (whole warp converged, election inside the asm) =================
+            {
                 const uint32_t tx = (uint32_t)p.rows_covered * rb * (uint32_t)p.slabs;
+                const uint32_t tiles0 = bl::smem_u32(tiles), full0 = bl::smem_u32(full), empty0 = bl::smem_u32(empty);
                 int s = 0;
                 uint32_t ph = 0;
-                for (int it = 0; it < iters; ++it, s = (s + 1 == p.stages) ? 0 : s + 1, ph ^= (s == 0) ? 1u : 0u) {
-                    bl::mbar_wait(&empty[s], ph ^ 1u);
-                    bl::mbar_arrive_expect_tx(&full[s], tx);
-                    uint8_t* dst = tiles + (size_t)s * stage_bytes;
-                    const int cf = p.row_bytes / 4;             // floats per slab row
+                const int cf = p.row_bytes / 4;             // floats per slab row
+                for (int it = 0; it < iters; ++it) {
+                    bl::mbar_wait_u32(empty0 + 8u * s, ph ^ 1u);
+                    const uint32_t fb = full0 + 8u * s;
+                    bl::mbar_arrive_expect_tx_e(fb, tx);
+                    const uint32_t dst = tiles0 + (uint32_t)s * stage_bytes;
                     const int c0 = (int)((kc0 + (long long)it * ksplits) * cf * p.slabs);
                     for (int sl = 0; sl < p.slabs; ++sl)
                         for (int b = 0; b < p.n_blocks; ++b)
-                            bl::tma_load_2d(dst + (size_t)sl * slab_bytes + (size_t)p.blk_smem_row[b] * rb,
-                                            &p.maps[b], &full[s], c0 + sl * cf, 0);
+                            bl::tma_load_2d_e(dst + (uint32_t)sl * slab_bytes + (uint32_t)p.blk_smem_row[b] * rb,
+                                              &p.maps[b], fb, c0 + sl * cf, 0);
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
             }
         } else if (warp == 1) {
             // ================= MMA issuer =================
             const int n_halves = (p.np_n + 255) / 256;
+            const uint32_t tiles0 = bl::smem_u32(tiles), ready0 = bl::smem_u32(ready), empty0 = bl::smem_u32(empty);
+            const uint32_t sbo = 8u * rb;            // 8-row swizzle atom
+            const uint32_t lay = (rb == 128u) ? bl::kLayoutSw128 : bl::kLayoutSw64;
+            const uint64_t d0 = bl::umma_smem_desc(tiles0, 16, sbo, lay);     // start-address field advances by adds
             int s = 0;
             uint32_t ph = 0;
-            for (int it = 0; it < iters; ++it, s = (s + 1 == p.stages) ? 0 : s + 1, ph ^= (s == 0) ? 1u : 0u) {
-                bl::mbar_wait(&ready[s], ph);
+            for (int it = 0; it < iters; ++it) {
+                bl::mbar_wait_u32(ready0 + 8u * s, ph);
                 bl::tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t hi0 = bl::smem_u32(tiles + (size_t)s * stage_bytes);
-                    for (int sl = 0; sl < ((p.dbg & 2) ? 0 : p.slabs); ++sl) {
+                const uint32_t hi0 = (uint32_t)s * stage_bytes;
+                for (int sl = 0; sl < ((p.dbg & 2) ? 0 : p.slabs); ++sl) {
                     const uint32_t hi = hi0 + (uint32_t)sl * slab_bytes;
                     const uint32_t lo = hi + tile_bytes;
                     for (int m = 0; m < nmb; ++m) {
@@ -154,27 +160,24 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
                             const uint32_t idesc = bl::umma_idesc_tf32(128, (uint32_t)ncols, 0, 0);
                             const uint32_t b_off = (uint32_t)h * 256u * rb;
                             const uint32_t d_tmem = tmem_base + (uint32_t)(m * p.np_n + h * 256);
-                            const uint32_t sbo = 8u * rb;            // 8-row swizzle atom
-                            const uint32_t lay = (rb == 128u) ? bl::kLayoutSw128 : bl::kLayoutSw64;
                             for (int k = 0; k < (int)(rb / 32u); ++k) {   // K = 8 tf32 = 32 B per MMA
                                 const uint32_t koff = (uint32_t)k * 32u;
-                                const uint64_t a_hi = bl::umma_smem_desc(hi + a_off + koff, 16, sbo, lay);
-                                const uint64_t b_hi = bl::umma_smem_desc(hi + b_off + koff, 16, sbo, lay);
-                                bl::umma_tf32(d_tmem, a_hi, b_hi, idesc, (it > 0 || sl > 0 || k > 0) ? 1u : 0u);
+                                const uint64_t a_hi = d0 + (uint64_t)((hi + a_off + koff) >> 4);
+                                const uint64_t b_hi = d0 + (uint64_t)((hi + b_off + koff) >> 4);
+                                bl::umma_tf32_e(d_tmem, a_hi, b_hi, idesc, (it > 0 || sl > 0 || k > 0) ? 1u : 0u);
                                 if (p.split3) {
-                                    const uint64_t a_lo = bl::umma_smem_desc(lo + a_off + koff, 16, sbo, lay);
-                                    const uint64_t b_lo = bl::umma_smem_desc(lo + b_off + koff, 16, sbo, lay);
-                                    bl::umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-                                    bl::umma_tf32(d_tmem, a_lo, b_hi, idesc, 1u);
+                                    const uint64_t a_lo = d0 + (uint64_t)((lo + a_off + koff) >> 4);
+                                    const uint64_t b_lo = d0 + (uint64_t)((lo + b_off + koff) >> 4);
+                                    bl::umma_tf32_e(d_tmem, a_hi, b_lo, idesc, 1u);
+                                    bl::umma_tf32_e(d_tmem, a_lo, b_hi, idesc, 1u);
                                 }
                             }
                         }
                     }
-                    }
-                    bl::umma_commit(&empty[s]);                    // smem slot reusable when MMAs retire
-                    if (it == iters - 1) bl::umma_commit(done);    // accumulators final
                 }
-                __syncwarp();
+                bl::umma_commit_e(empty0 + 8u * s);                    // smem slot reusable when MMAs retire
+                if (it == iters - 1) bl::umma_commit_e(bl::smem_u32(done));    // accumulators final
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         } else {
             // ================= converter (warps 2..5) =================

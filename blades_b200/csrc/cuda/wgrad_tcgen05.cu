@@ -61,7 +61,7 @@ wgrad_tcgen05_kernel(const __grid_constant__ WgradParams p) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
     float* epi = reinterpret_cast<float*>(tiles + (size_t)p.stages * stage_bytes + 256);   // 4 x [32][kEpiLd]
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = bl::uniform_warp_idx(), lane = threadIdx.x & 31;
     const long long total_tiles = (long long)p.n_clients * p.m_tiles * p.n_tiles;
     const int ksteps = p.T / p.KT;
 
@@ -77,50 +77,53 @@ wgrad_tcgen05_kernel(const __grid_constant__ WgradParams p) {
     __syncthreads();
     bl::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tiles0 = bl::smem_u32(tiles);
+    const uint32_t full0 = bl::smem_u32(full), empty0 = bl::smem_u32(empty);
+    const uint32_t tfull0 = bl::smem_u32(tfull), tempty0 = bl::smem_u32(tempty);
 
+    // Warps 0 and 1 run their loops CONVERGED (all lanes, uniform values, election inside the asm): see tc_common.cuh
+    // "warp-uniform issue".  Stage / parity are running counters (no integer divisions in the issue loops).
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
-            int s = 0;                      // running stage / parity: no integer divisions in the issue loops
-            uint32_t ph = 0;
-            const int hchunks = p.implicit ? p.Ho / p.bh : 1;
-            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = (int)(tile % p.n_tiles);
-                const int mt = (int)((tile / p.n_tiles) % p.m_tiles);
-                const int c = (int)(tile / ((long long)p.n_tiles * p.m_tiles));
-                int kb = 0, kh = 0;         // implicit mode: sample-group / row-chunk counters of the K step
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    bl::mbar_wait(&empty[s], ph ^ 1u);
-                    bl::mbar_arrive_expect_tx(&full[s], stage_bytes);
-                    uint8_t* dst = tiles + (size_t)s * stage_bytes;
-                    const int row = c * p.T + ks * p.KT;
+        int s = 0;
+        uint32_t ph = 0;
+        const int hchunks = p.implicit ? p.Ho / p.bh : 1;
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = (int)(tile % p.n_tiles);
+            const int mt = (int)((tile / p.n_tiles) % p.m_tiles);
+            const int c = (int)(tile / ((long long)p.n_tiles * p.m_tiles));
+            int kb = 0, kh = 0;         // implicit mode: sample-group / row-chunk counters of the K step
+            for (int ks = 0; ks < ksteps; ++ks) {
+                bl::mbar_wait_u32(empty0 + 8u * s, ph ^ 1u);
+                const uint32_t fb = full0 + 8u * s;
+                bl::mbar_arrive_expect_tx_e(fb, stage_bytes);
+                const uint32_t dst = tiles0 + (uint32_t)s * stage_bytes;
+                const int row = c * p.T + ks * p.KT;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        bl::tma_load_2d(dst + j * box_bytes, &p.map_a, &full[s], mt * 128 + j * 32, row);
-                    if (!p.implicit) {
-                        for (uint32_t j = 0; j < nb_blocks; ++j)
-                            bl::tma_load_2d(dst + a_bytes + j * box_bytes, &p.map_b, &full[s],
-                                            nt * p.BN + (int)j * 32, row);
-                    } else {
-                        // K chunk ks = output positions (b0..b0+bb) x (ho0..ho0+bh) x (0..Wo) of client c; for the
-                        // 32-channel block (tap, cin0) the matching input pixels are one strided 4-D TMA box; conv
-                        // padding = out-of-range coordinates, zero-filled by TMA.
-                        const int b0 = kb * p.bb, ho0 = kh * p.bh;
-                        int n0 = nt * p.BN;
-                        int tap = n0 / p.Cin, cin0 = n0 - tap * p.Cin;          // one division per K step, then running
-                        int r = tap / p.kw, sx = tap - r * p.kw;
-                        for (uint32_t j = 0; j < nb_blocks; ++j) {
-                            const bool valid = tap < p.taps;
-                            bl::tma_load_4d(dst + a_bytes + j * box_bytes, &p.map_x, &full[s],
-                                            valid ? cin0 : p.Cin,           // beyond the channel extent -> zeros
-                                            sx - p.cp, ho0 * p.cs + r - p.cp, c * p.Bc + b0);
-                            cin0 += 32;
-                            if (cin0 >= p.Cin) { cin0 = 0; ++tap; if (++sx == p.kw) { sx = 0; ++r; } }
-                        }
-                        if (++kh == hchunks) { kh = 0; ++kb; }
+                for (int j = 0; j < 4; ++j)
+                    bl::tma_load_2d_e(dst + j * box_bytes, &p.map_a, fb, mt * 128 + j * 32, row);
+                if (!p.implicit) {
+                    for (uint32_t j = 0; j < nb_blocks; ++j)
+                        bl::tma_load_2d_e(dst + a_bytes + j * box_bytes, &p.map_b, fb, nt * p.BN + (int)j * 32, row);
+                } else {
+                    // K chunk ks = output positions (b0..b0+bb) x (ho0..ho0+bh) x (0..Wo) of client c; for the
+                    // 32-channel block (tap, cin0) the matching input pixels are one strided 4-D TMA box; conv
+                    // padding = out-of-range coordinates, zero-filled by TMA.
+                    const int b0 = kb * p.bb, ho0 = kh * p.bh;
+                    int n0 = nt * p.BN;
+                    int tap = n0 / p.Cin, cin0 = n0 - tap * p.Cin;          // one division per K step, then running
+                    int r = tap / p.kw, sx = tap - r * p.kw;
+                    for (uint32_t j = 0; j < nb_blocks; ++j) {
+                        const bool valid = tap < p.taps;
+                        bl::tma_load_4d_e(dst + a_bytes + j * box_bytes, &p.map_x, fb,
+                                          valid ? cin0 : p.Cin,           // beyond the channel extent -> zeros
+                                          sx - p.cp, ho0 * p.cs + r - p.cp, c * p.Bc + b0);
+                        cin0 += 32;
+                        if (cin0 >= p.Cin) { cin0 = 0; ++tap; if (++sx == p.kw) { sx = 0; ++r; } }
                     }
-                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                    if (++kh == hchunks) { kh = 0; ++kb; }
                 }
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
@@ -129,30 +132,26 @@ wgrad_tcgen05_kernel(const __grid_constant__ WgradParams p) {
         uint32_t tcount = 0;
         int s = 0;
         uint32_t ph = 0;
-        const uint32_t tiles0 = bl::smem_u32(tiles);
+        // MN-major tf32: SWIZZLE_128B_BASE32B; LBO = stride between 32-float column blocks, SBO = stride between 4-row
+        // K atoms (rows are contiguous: 512 B); one 8-row K atom (1024 B) per MMA.  The start-address field of the
+        // descriptors (address >> 4) advances by plain adds.
         const uint64_t ad0 = bl::umma_smem_desc(tiles0, box_bytes, 512u, bl::kLayoutSw128Base32B);
         const uint64_t bd0 = bl::umma_smem_desc(tiles0 + a_bytes, box_bytes, 512u, bl::kLayoutSw128Base32B);
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
             const uint32_t buf = tcount & 1u;
             const uint32_t tph = (tcount >> 1) & 1u;
-            bl::mbar_wait(&tempty[buf], tph ^ 1u);             // epilogue drained this accumulator
+            bl::mbar_wait_u32(tempty0 + 8u * buf, tph ^ 1u);             // epilogue drained this accumulator
             bl::tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * 256u;
             for (int ks = 0; ks < ksteps; ++ks) {
-                bl::mbar_wait(&full[s], ph);
+                bl::mbar_wait_u32(full0 + 8u * s, ph);
                 bl::tc_fence_after();
-                if (lane == 0) {
-                    // MN-major tf32: SWIZZLE_128B_BASE32B; LBO = stride between 32-float column blocks, SBO = stride
-                    // between 4-row K atoms (rows are contiguous: 512 B); one 8-row K atom (1024 B) per MMA.  The
-                    // start-address field of the descriptors (address >> 4) advances by plain adds.
-                    const uint64_t so = (uint64_t)(((uint32_t)s * stage_bytes) >> 4);
-                    for (int ka = 0; ka < p.KT / 8; ++ka)
-                        bl::umma_tf32(d_tmem, ad0 + so + (uint64_t)(ka * 64), bd0 + so + (uint64_t)(ka * 64), idesc,
-                                      (ks > 0 || ka > 0) ? 1u : 0u);
-                    bl::umma_commit(&empty[s]);
-                    if (ks == ksteps - 1) bl::umma_commit(&tfull[buf]);
-                }
-                __syncwarp();
+                const uint64_t so = (uint64_t)(((uint32_t)s * stage_bytes) >> 4);
+                for (int ka = 0; ka < p.KT / 8; ++ka)
+                    bl::umma_tf32_e(d_tmem, ad0 + so + (uint64_t)(ka * 64), bd0 + so + (uint64_t)(ka * 64), idesc,
+                                    (ks > 0 || ka > 0) ? 1u : 0u);
+                bl::umma_commit_e(empty0 + 8u * s);
+                if (ks == ksteps - 1) bl::umma_commit_e(tfull0 + 8u * buf);
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
