@@ -149,38 +149,46 @@ struct ClientCEParams {
     const long long* target; // [n*B]
     const float* clamp;      // [n]
     float* loss;             // [n]  (unclamped mean, like the reference logs it)
-    float* dlogits;          // [n*B][ldg]; columns >= C are written as zeros
+    float* dlogits;          // [n*B][ldg]; columns >= C are written as zeros (nullptr: evaluation only)
+    float* hits;             // optional [n]: number of samples whose argmax equals the target (top-1 evaluation)
     int n, B, C, ldl, ldg;
 };
 
 __global__ void __launch_bounds__(128)
 client_ce_kernel(const __grid_constant__ ClientCEParams p) {
     __shared__ float red[128];
+    __shared__ float redh[128];
     __shared__ float s_scale;
     const int c = blockIdx.x;
-    float local = 0.f;
+    float local = 0.f, nhit = 0.f;
     for (int b = threadIdx.x; b < p.B; b += blockDim.x) {
         const float* z = p.logits + (long long)(c * p.B + b) * p.ldl;
         float m = -INFINITY;
-        for (int j = 0; j < p.C; ++j) m = fmaxf(m, z[j]);
+        int am = 0;
+        for (int j = 0; j < p.C; ++j)
+            if (z[j] > m) { m = z[j]; am = j; }              // first maximum, like torch.argmax
         float se = 0.f;
         for (int j = 0; j < p.C; ++j) se += expf(z[j] - m);
         const long long t = p.target[c * p.B + b];
         const float zt = (t >= 0 && t < p.C) ? z[t] : 0.f;
         local += (m + logf(se)) - zt;
+        nhit += (am == t) ? 1.f : 0.f;
     }
     red[threadIdx.x] = local;
+    redh[threadIdx.x] = nhit;
     __syncthreads();
     for (int o = 64; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        if ((int)threadIdx.x < o) { red[threadIdx.x] += red[threadIdx.x + o]; redh[threadIdx.x] += redh[threadIdx.x + o]; }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         const float mean = red[0] / (float)p.B;
         p.loss[c] = mean;
+        if (p.hits != nullptr) p.hits[c] = redh[0];
         // d/dx min(max(x, 0), clamp): 1 inside (0, clamp); NaN losses give no gradient
-        s_scale = (mean > 0.f && mean < p.clamp[c]) ? 1.f / (float)p.B : 0.f;
+        s_scale = (p.clamp != nullptr && mean > 0.f && mean < p.clamp[c]) ? 1.f / (float)p.B : 0.f;
     }
+    if (p.dlogits == nullptr) return;
     __syncthreads();
     const float scale = s_scale;
     for (int b = threadIdx.x; b < p.B; b += blockDim.x) {
@@ -200,9 +208,9 @@ client_ce_kernel(const __grid_constant__ ClientCEParams p) {
     }
 }
 extern "C" int bl_client_ce(const float* logits, const long long* target, const float* clamp, float* loss,
-                            float* dlogits, int n, int B, int C, int ldl, int ldg, void* stream) {
-    if (n < 1 || B < 1 || C < 1 || ldg < C || ldl < C) return -1;
-    ClientCEParams p{logits, target, clamp, loss, dlogits, n, B, C, ldl, ldg};
+                            float* dlogits, float* hits, int n, int B, int C, int ldl, int ldg, void* stream) {
+    if (n < 1 || B < 1 || C < 1 || (dlogits != nullptr && ldg < C) || ldl < C) return -1;
+    ClientCEParams p{logits, target, clamp, loss, dlogits, hits, n, B, C, ldl, ldg};
     client_ce_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(p);
     return (int)cudaGetLastError();
 }

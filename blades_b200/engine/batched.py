@@ -90,6 +90,13 @@ class _LinearFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, sink, wname, bname):
         ctx.save_for_backward(x, weight)
         ctx.sink, ctx.wname, ctx.bname = sink, wname, bname
+        if x.is_cuda and x.dtype == torch.float32:
+            # own tcgen05 GEMM (a 1x1 convolution over 1x1 images); declines odd strides / alignments
+            from ..ops import conv as kc
+            x2 = x.reshape(-1, x.shape[-1])
+            y = kc.linear_fprop(x2, weight, bias) if x2.is_contiguous() else None
+            if y is not None:
+                return y.reshape(tuple(x.shape[:-1]) + (weight.shape[0],))
         return F.linear(x, weight, bias)
 
     @staticmethod
@@ -104,15 +111,34 @@ class _LinearFn(torch.autograd.Function):
         sink.put_bmm(ctx.wname, gy2.view(n, T, -1).transpose(1, 2), x2.view(n, T, -1))
         if ctx.bname is not None:
             sink.put(ctx.bname, gy2.view(n, T, -1).sum(1))
-        gx = gy @ weight if ctx.needs_input_grad[0] else None
+        gx = None
+        if ctx.needs_input_grad[0]:
+            if gy2.is_cuda and gy2.dtype == torch.float32:
+                from ..ops import conv as kc
+                g2 = kc.linear_dgrad(gy2, weight)
+                if g2 is not None:
+                    gx = g2.reshape(x.shape)
+            if gx is None:
+                gx = gy @ weight
         return gx, None, None, None, None, None
 
 
-def _conv_dgrad(gy, x, weight, stride, padding, dilation):
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+def _conv_dgrad(gy, x, weight, stride, padding, dilation, w2d=None):
     """Input gradient of conv2d.  ``torch.nn.grad.conv2d_input`` hands cuDNN a stride-0 dummy of the input's
     shape, which the backend then materialises with ``.contiguous()`` -- a full activation-sized copy per layer
     (measured: 20 copies, 0.31 ms of an 11 ms ResNet-18 round).  Passing the real saved input costs nothing and
     keeps the result channels_last."""
+    if w2d is not None:                 # the forward ran on the own tcgen05 kernel: so does the input gradient
+        from ..ops import conv as kc
+        gx = kc.conv_dgrad(gy.contiguous(memory_format=torch.channels_last), w2d, tuple(weight.shape[2:]),
+                           _pair(stride)[0], _pair(padding)[0], tuple(x.shape[2:]), x.shape[1])
+        if gx is not None:
+            return gx
+
     def pair(v):
         return [v, v] if isinstance(v, int) else list(v)
     return torch.ops.aten.convolution_backward(gy, x, weight, None, pair(stride), pair(padding), pair(dilation),
@@ -130,6 +156,17 @@ class _ConvFn(torch.autograd.Function):
         ctx.save_for_backward(x, weight)
         ctx.sink, ctx.wname, ctx.bname = sink, wname, bname
         ctx.conf = (stride, padding, dilation)
+        ctx.w2d = None
+        if x.is_cuda and sink.channels_last:
+            from ..ops import conv as kc
+            if kc.supported_conv(x, weight, _pair(stride), _pair(padding), _pair(dilation)):
+                wp = weight.permute(0, 2, 3, 1)
+                if wp.is_contiguous():                         # physical layout = channels_last: [Cout, kh*kw*Cin] view
+                    w2d = wp.reshape(weight.shape[0], -1)
+                    y = kc.conv_fprop(x, w2d, tuple(weight.shape[2:]), _pair(stride)[0], _pair(padding)[0], bias=bias)
+                    if y is not None:
+                        ctx.w2d = w2d
+                        return y
         return F.conv2d(x, weight, bias, stride, padding, dilation, 1)
 
     @staticmethod
@@ -156,7 +193,7 @@ class _ConvFn(torch.autograd.Function):
                         sink.put(ctx.bname, gy.reshape(n, B, Cout, L).sum((1, 3)))
                     gx = None
                     if ctx.needs_input_grad[0]:
-                        gx = _conv_dgrad(gy, x, weight, stride, padding, dilation)
+                        gx = _conv_dgrad(gy, x, weight, stride, padding, dilation, ctx.w2d)
                     return gx, None, None, None, None, None, None, None, None
             cols = im2col_nhwc(x, (kh, kw), stride, padding, dilation, (Ho, Wo))      # [NB*L, K] (padded rows)
             b = cols.as_strided((n, B * L, cols.shape[1]), (B * L * cols.stride(0), cols.stride(0), 1))
@@ -169,7 +206,7 @@ class _ConvFn(torch.autograd.Function):
             sink.put(ctx.bname, gy.reshape(n, B, Cout, L).sum((1, 3)))
         gx = None
         if ctx.needs_input_grad[0]:
-            gx = _conv_dgrad(gy, x, weight, stride, padding, dilation)
+            gx = _conv_dgrad(gy, x, weight, stride, padding, dilation, ctx.w2d)
         return gx, None, None, None, None, None, None, None, None
 
 
@@ -396,6 +433,14 @@ def batched_step(model: nn.Module, sink: GradSink, x: torch.Tensor, y: torch.Ten
         return rf.step(model, sink, x, y, n, clamp)
     with client_batched(model, sink, x.shape[0]):
         logits = model(x)
-        loss, per_client = batched_loss(logits, y, n, clamp)
-        loss.backward()
+        if logits.is_cuda and logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1 \
+                and y.dtype == torch.int64 and sink.out.dtype == torch.float32:
+            # per-client clamped mean cross-entropy and its logits gradient in ONE own launch; the gradient rows are
+            # padded to 16 B so the classifier's input-gradient GEMM can read them by TMA
+            from ..ops import fused as kf
+            per_client, g = kf.client_ce(logits.detach(), y.contiguous(), n, clamp)
+            logits.backward(g)
+        else:
+            loss, per_client = batched_loss(logits, y, n, clamp)
+            loss.backward()
     return per_client

@@ -29,13 +29,12 @@ from ..ops import fused as kf
 from ..ops import wgrad as kw
 from ..ops.im2col import im2col_nhwc
 
-__all__ = ["supports", "step"]
+__all__ = ["supports", "supports_eval", "step", "forward_logits"]
 
 
-def supports(model: nn.Module, sink, x: torch.Tensor) -> bool:
+def _model_ok(model: nn.Module, x: torch.Tensor) -> bool:
     if not (kc.ENABLED and isinstance(model, ResNet) and model.norm_kind == "batch" and x.is_cuda
-            and x.dtype == torch.float32 and sink.channels_last and sink.out.dtype == torch.float32
-            and model.training):
+            and x.dtype == torch.float32):
         return False
     if type(model.maxpool) is not nn.MaxPool2d or model.fc.bias is None:
         return False
@@ -44,8 +43,22 @@ def supports(model: nn.Module, sink, x: torch.Tensor) -> bool:
             return False
         if isinstance(m, nn.BatchNorm2d) and (m.track_running_stats or not m.affine):
             return False
-    theta_ok = all(p.data_ptr() % 16 == 0 for name, p in model.named_parameters() if p.dim() > 1)
-    return theta_ok
+    for name, p in model.named_parameters():
+        if p.dim() > 1 and (p.data_ptr() % 16 or p.dtype != torch.float32):
+            return False
+        if p.dim() == 4 and not p.data.permute(0, 2, 3, 1).is_contiguous():      # physical layout = channels_last
+            return False
+    return True
+
+
+def supports(model: nn.Module, sink, x: torch.Tensor) -> bool:
+    return bool(model.training and sink.channels_last and sink.out.dtype == torch.float32 and _model_ok(model, x))
+
+
+def supports_eval(model: nn.Module, x: torch.Tensor) -> bool:
+    """Forward-only use (evaluation): the model's BatchNorms have no running statistics, so ``model.eval()`` still
+    normalises with the statistics of each forward batch -- exactly the per-group statistics of the fused pass."""
+    return _model_ok(model, x)
 
 
 class _Unit:
@@ -61,8 +74,9 @@ def _w2d(conv: nn.Conv2d) -> torch.Tensor:
 
 
 class _Pass:
-    def __init__(self, model: ResNet, sink, n: int):
+    def __init__(self, model: ResNet, sink, n: int, keep: bool = True):
         self.model, self.sink, self.n = model, sink, n
+        self.keep = keep            # False: forward only -- drop what the backward pass would need
         self.names = {id(m): name for name, m in model.named_modules()}
 
     # ---------------------------------------------------------------- forward pieces
@@ -104,6 +118,8 @@ class _Pass:
         u.c = self.conv_fwd(u, x)
         u.y, u.mean, u.rstd = kbn.forward(u.c, bn.weight.data, bn.bias.data, self.n, bn.eps, res=res, relu=relu,
                                           nhwc=True)
+        if not self.keep:
+            u.x = u.c = u.cols = None
         return u
 
     # ---------------------------------------------------------------- backward pieces
@@ -184,32 +200,44 @@ def _block_bwd(ps: _Pass, saved, g: torch.Tensor) -> torch.Tensor:
     return ps.dgrad(ds, gcd, add=gx, out=gx)                        # accumulate the shortcut's share in place
 
 
+def _forward(ps: _Pass, x: torch.Tensor):
+    model = ps.model
+    stem = ps.unit_fwd(model.conv1, model.bn1, x, relu=True)
+    mp = model.maxpool
+    as_int = lambda v: v if isinstance(v, int) else v[0]
+    k, st, pd = as_int(mp.kernel_size), as_int(mp.stride), as_int(mp.padding)
+    h, pool_idx = kf.maxpool_fwd(stem.y, k, st, pd)
+    saved = []
+    for layer in (model.layer1, model.layer2, model.layer3, model.layer4):
+        for blk in layer:
+            h, sv = _block_fwd(ps, blk, h)
+            saved.append(sv if ps.keep else None)
+    NB, Cf, Hf, Wf = h.shape
+    feat = h.reshape(NB, Cf) if Hf * Wf == 1 else kf.avgpool_fwd(h)
+    if Hf * Wf == 1:
+        assert feat.data_ptr() == h.data_ptr()
+    logits = kc.linear_fprop(feat, model.fc.weight.data, model.fc.bias.data)
+    if logits is None:
+        raise RuntimeError("linear_fprop declined the classifier")
+    return logits, feat, (Hf, Wf), saved, stem, pool_idx, (k, st, pd)
+
+
+def forward_logits(model: ResNet, x: torch.Tensor, n_groups: int) -> torch.Tensor:
+    """Forward only: logits of ``x`` (``[n_groups*B, Cin, H, W]``) with BatchNorm statistics taken per group of B
+    samples -- what ``model(x_group)`` computes group by group (evaluation, reference client.py:144-176)."""
+    with torch.no_grad():
+        return _forward(_Pass(model, None, n_groups, keep=False), x)[0]
+
+
 def step(model: ResNet, sink, x: torch.Tensor, y: torch.Tensor, n: int, clamp: torch.Tensor) -> torch.Tensor:
     """One fedsgd step of ``n`` clients (x: ``[n*B, Cin, H, W]`` in any layout, y: ``[n*B]`` int64): fills the rows of
     ``sink.out`` with ``-lr * grad_c`` and returns the per-client mean losses."""
     ps = _Pass(model, sink, n)
     s = sink
     with torch.no_grad():
-        # ------------------------------------------------------------------ forward
-        stem = ps.unit_fwd(model.conv1, model.bn1, x, relu=True)
-        mp = model.maxpool
-        k, st, pd = (mp.kernel_size, mp.stride, mp.padding)
-        k, st, pd = (k if isinstance(k, int) else k[0]), (st if isinstance(st, int) else st[0]), \
-            (pd if isinstance(pd, int) else pd[0])
-        h, pool_idx = kf.maxpool_fwd(stem.y, k, st, pd)
-        saved = []
-        for layer in (model.layer1, model.layer2, model.layer3, model.layer4):
-            for blk in layer:
-                h, sv = _block_fwd(ps, blk, h)
-                saved.append(sv)
-        NB, Cf, Hf, Wf = h.shape
-        feat = h.reshape(NB, Cf) if Hf * Wf == 1 else kf.avgpool_fwd(h)
-        if Hf * Wf == 1:
-            assert feat.data_ptr() == h.data_ptr()
+        logits, feat, (Hf, Wf), saved, stem, pool_idx, (k, st, pd) = _forward(ps, x)
+        NB, Cf = feat.shape
         fc = model.fc
-        logits = kc.linear_fprop(feat, fc.weight.data, fc.bias.data)
-        if logits is None:
-            raise RuntimeError("linear_fprop declined the classifier")
         loss, glogits = kf.client_ce(logits, y, n, clamp)
         # ------------------------------------------------------------------ backward
         T = NB // n

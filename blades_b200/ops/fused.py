@@ -11,7 +11,8 @@ import torch
 
 from . import _loader
 
-__all__ = ["maxpool_fwd", "maxpool_bwd", "avgpool_fwd", "avgpool_bwd", "client_ce", "client_colsum", "pad_rows"]
+__all__ = ["maxpool_fwd", "maxpool_bwd", "avgpool_fwd", "avgpool_bwd", "client_ce", "group_eval", "client_colsum",
+           "pad_rows"]
 
 _typed = False
 
@@ -25,7 +26,7 @@ def _lib():
         lib.bl_maxpool_nhwc_bwd.argtypes = [vp, vp, vp] + [i] * 9 + [vp]
         lib.bl_avgpool_nhwc_fwd.argtypes = [vp, vp, ll, i, i, vp]
         lib.bl_avgpool_nhwc_bwd.argtypes = [vp, vp, ll, i, i, vp]
-        lib.bl_client_ce.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, vp]
+        lib.bl_client_ce.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp]
         lib.bl_client_colsum.argtypes = [vp, vp, i, i, i, ll, ll, f, vp]
         lib.bl_pad_rows.argtypes = [vp, vp, ll, i, ll, i, vp]
         _typed = True
@@ -88,10 +89,24 @@ def client_ce(logits: torch.Tensor, target: torch.Tensor, n: int, clamp: torch.T
     loss = torch.empty(n, device=logits.device, dtype=torch.float32)
     g = torch.empty(M, ldg, device=logits.device, dtype=torch.float32)
     _loader.check(_lib().bl_client_ce(logits.data_ptr(), target.data_ptr(), clamp.data_ptr(), loss.data_ptr(),
-                                      g.data_ptr(), n, M // n, Cc, logits.stride(0), ldg,
+                                      g.data_ptr(), None, n, M // n, Cc, logits.stride(0), ldg,
                                       _loader.stream_ptr(logits.device)), "client_ce")
     _loader.count_launch()
     return loss, g[:, :Cc]
+
+
+def group_eval(logits: torch.Tensor, target: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Evaluation twin of ``client_ce``: per-group mean cross-entropy ``[n]`` and top-1 hit counts ``[n]`` of ``n``
+    equally sized groups of samples (one launch, no gradient)."""
+    M, Cc = logits.shape
+    assert logits.stride(1) == 1 and target.dtype == torch.int64 and target.is_contiguous() and M % n == 0
+    loss = torch.empty(n, device=logits.device, dtype=torch.float32)
+    hits = torch.empty(n, device=logits.device, dtype=torch.float32)
+    _loader.check(_lib().bl_client_ce(logits.data_ptr(), target.data_ptr(), None, loss.data_ptr(), None,
+                                      hits.data_ptr(), n, M // n, Cc, logits.stride(0), 0,
+                                      _loader.stream_ptr(logits.device)), "group_eval")
+    _loader.count_launch()
+    return loss, hits
 
 
 def client_colsum(g: torch.Tensor, n: int, out_view: torch.Tensor, alpha: float) -> None:

@@ -360,7 +360,9 @@ class Simulator(object):
         """Evaluate the global model on every client's test shard (length-weighted)."""
         eng = self.engine
         model = self.server.get_model()
-        records = self._test_batched(global_round, batch_size)
+        records = self._test_fused(global_round, batch_size)
+        if records is None:
+            records = self._test_batched(global_round, batch_size)
         if records is None:
             records = []
             for gi in eng.local_idx:
@@ -373,6 +375,87 @@ class Simulator(object):
         loss, top1 = self.log_validate(records)
         self.debug_logger.info(f"Test global round {global_round}, loss: {loss}, top1: {top1}")
         return loss, top1
+
+    def _eval_shards(self, clients):
+        """Device-resident copies of the local test shards (cached): ``(X, y, lens)`` or None when a shard is not a
+        deterministic tensor dataset."""
+        from .datasets.customdataset import CustomTensorDataset
+        cache = getattr(self, "_eval_cache", None)
+        if cache is None:
+            xs, ys, lens = [], [], []
+            for c in clients:
+                ds = self.dataset.get_all_test_data(c.id())
+                if not isinstance(ds, CustomTensorDataset) or not ds.deterministic:
+                    return None
+                x, y = ds.tensors
+                if ds.transforms is not None and len(x):
+                    x = torch.stack([ds.transforms(xi) for xi in x])
+                xs.append(x), ys.append(y), lens.append(len(y))
+            if min(lens) == 0:
+                return None
+            dev = self.engine.device
+            seg = torch.repeat_interleave(torch.arange(len(lens)), torch.tensor(lens))
+            cache = self._eval_cache = (torch.cat(xs).to(dev), torch.cat(ys).to(dev), seg.to(dev), lens)
+        return cache
+
+    def _test_fused(self, global_round, batch_size):
+        """Evaluation of the ResNet family through the own-kernel forward pass (``engine/resnet_fused.py``; SURVEY
+        K10).  The reference evaluates client by client in batches of ``batch_size`` (client.py:144-176); these models
+        normalise with the statistics of every forward batch, so the grouping matters: each evaluation batch of the
+        reference becomes one statistics group of ONE fused forward over all local clients' test data (batches of the
+        same size share a launch; the shorter tail batches of the shards form a second one).  Same per-client
+        records, one host sync.  Returns None when the conditions do not hold."""
+        import torch.nn as nn
+
+        eng = self.engine
+        clients = [self.get_clients()[gi] for gi in eng.local_idx]
+        if not clients or eng.device.type != "cuda" or set(self.metrics) != {"top1"} \
+                or self.metrics["top1"] is not top1_accuracy:
+            return None
+        from .engine.round import _default_ce
+        if any(type(c).evaluate is not BladesClient.evaluate or not _default_ce(c.loss_func) for c in clients):
+            return None
+        model = self.server.get_model()
+        from .engine import resnet_fused as rf
+        shards = self._eval_shards(clients)
+        if shards is None or not rf.supports_eval(model, shards[0]):
+            return None
+        X, y, _, lens = shards
+        from .ops import fused as kf
+        bs = int(batch_size)
+        # contiguous runs of equally sized evaluation batches: (first sample, batch size, owners of the batches).  The
+        # shards sit back to back in X, so the full batches of consecutive clients form ONE run (a slice, no gather)
+        # unless a shorter tail batch interrupts it.
+        runs, start = [], 0
+        for j, n in enumerate(lens):
+            for o in range(0, n, bs):
+                size = min(bs, n - o)
+                if runs and runs[-1][1] == size and runs[-1][0] + size * len(runs[-1][2]) == start + o:
+                    runs[-1][2].append(j)
+                else:
+                    runs.append((start + o, size, [j]))
+            start += n
+        max_groups = max(1, 8192 // bs)                                    # bound the activation footprint
+        pending = []
+        for first, size, owners in runs:
+            for g0 in range(0, len(owners), max_groups):
+                part = owners[g0: g0 + max_groups]
+                a = first + g0 * size
+                b = a + len(part) * size
+                logits = rf.forward_logits(model, X[a:b], len(part))
+                gl, gh = kf.group_eval(logits, y[a:b], len(part))
+                pending.append((part, size, gl, gh))
+        stats = np.zeros((2, len(lens)))
+        for part, size, gl, gh in pending:                           # host syncs only after everything is queued
+            np.add.at(stats[0], part, gl.cpu().numpy().astype(np.float64) * size)
+            np.add.at(stats[1], part, gh.cpu().numpy().astype(np.float64))
+        records = []
+        for j, c in enumerate(clients):
+            rec = {"_meta": {"type": "client_validation"}, "E": global_round, "Length": lens[j],
+                   "Loss": float(stats[0, j]) / lens[j], "top1": 100.0 * float(stats[1, j]) / lens[j]}
+            c._json_logger.info(rec)
+            records.append(rec)
+        return records
 
     def _test_batched(self, global_round, batch_size):
         """Evaluation fast path: the reference evaluates client by client in batches of
@@ -396,24 +479,9 @@ class Simulator(object):
         model = self.server.get_model()
         if any(isinstance(m, nn.modules.batchnorm._BatchNorm) and not m.track_running_stats for m in model.modules()):
             return None
-        cache = getattr(self, "_eval_cache", None)
+        cache = self._eval_shards(clients)
         if cache is None:
-            xs, ys, lens = [], [], []
-            for c in clients:
-                ds = self.dataset.get_all_test_data(c.id())
-                if not isinstance(ds, CustomTensorDataset):
-                    return None
-                x, y = ds.tensors
-                if not ds.deterministic:
-                    return None
-                if ds.transforms is not None and len(x):
-                    x = torch.stack([ds.transforms(xi) for xi in x])
-                xs.append(x), ys.append(y), lens.append(len(y))
-            if min(lens) == 0:
-                return None
-            dev = eng.device
-            seg = torch.repeat_interleave(torch.arange(len(lens)), torch.tensor(lens))
-            cache = self._eval_cache = (torch.cat(xs).to(dev), torch.cat(ys).to(dev), seg.to(dev), lens)
+            return None
         X, y, seg, lens = cache
         was_training = model.training
         model.eval()

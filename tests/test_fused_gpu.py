@@ -241,3 +241,27 @@ def test_fused_resnet_step_launches_only_own_kernels():
     assert names and not foreign, foreign
     total = sum(e.count for e in prof.key_averages() if e.device_type == torch.autograd.DeviceType.CUDA)
     assert total <= 130, total
+
+
+def test_fused_evaluation_matches_the_per_client_loop(tmp_path):
+    """K10: evaluation of a batch-statistics ResNet through the own-kernel forward (one statistics group per reference
+    evaluation batch, tail batches included) vs the reference-style per-client ``evaluate`` loop."""
+    from blades_b200 import Simulator
+    from blades_b200.datasets import synthetic_fldataset
+    from blades_b200.models import resnet18
+    ds = synthetic_fldataset(5, shape=(3, 32, 32), num_classes=10, train_bs=8, train_per_client=16, test_per_client=20,
+                             seed=2, separation=1.5)
+    sim = Simulator(ds, aggregator="mean", use_cuda=True, seed=1, log_path=str(tmp_path), progress=False)
+    model = resnet18(10)
+    sim.prepare(model, "SGD", "SGD", "crossentropy", server_lr=1.0, client_lr=0.05)
+    sim.train_actor(0, 1, sim.get_clients(), 0.05)
+    fused = sim._test_fused(0, 8)
+    assert fused is not None and len(fused) == 5
+    m = sim.server.get_model()
+    for rec, c in zip(fused, sim.get_clients()):
+        ref = c.evaluate(round_number=0, test_set=ds.get_all_test_data(c.id()), batch_size=8, metrics=sim.metrics,
+                         use_actor=True, model=m)
+        assert rec["Length"] == ref["Length"] == 20
+        assert abs(rec["Loss"] - ref["Loss"]) < 2e-2 * max(1.0, abs(ref["Loss"]))
+        assert abs(rec["top1"] - ref["top1"]) <= 10.0 + 1e-6           # at most 2 of 20 borderline samples flip
+    m.train()
