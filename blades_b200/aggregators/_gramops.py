@@ -38,7 +38,7 @@ def _native():
 
 
 __all__ = [
-    "sq_dists", "dist_to_combo", "krum_scores", "multi_krum_select", "weiszfeld_weights",
+    "sq_dists", "dist_to_combo", "krum_scores", "check_krum_args", "multi_krum_select", "weiszfeld_weights",
     "autogm_weights", "centered_clip_coeffs", "cosine_matrix", "complete_linkage_2",
     "majority_cluster", "fltrust_weights",
 ]
@@ -79,16 +79,21 @@ def krum_scores(D: np.ndarray, f: int, n: Optional[int] = None, squared_twice: b
     return part.sum(axis=1)
 
 
-def multi_krum_select(D: np.ndarray, f: int, m: int = 1, n: Optional[int] = None,
-                      squared_twice: bool = False) -> List[int]:
-    """Indices of the ``m`` best-scoring rows (stable order, like ``sorted``)."""
-    n = D.shape[0] if n is None else n
+def check_krum_args(n: int, f: int, m: int) -> None:
+    """The reference's argument checks (krum.py:96-110), shared by the host and the device selection."""
     if n < 1:
         raise ValueError(f"Number of workers should be positive integer. Got {n}.")
     if m < 1 or m > n:
         raise ValueError(f"Number of workers for aggregation should be >=1 and <= {n}. Got {m}.")
     if 2 * f + 2 > n:
         raise ValueError(f"Too many Byzantine workers: 2 * {f} + 2 >= {n}.")
+
+
+def multi_krum_select(D: np.ndarray, f: int, m: int = 1, n: Optional[int] = None,
+                      squared_twice: bool = False) -> List[int]:
+    """Indices of the ``m`` best-scoring rows (stable order, like ``sorted``)."""
+    n = D.shape[0] if n is None else n
+    check_krum_args(n, f, m)
     scores = krum_scores(D, f, n, squared_twice)
     order = np.argsort(scores, kind="stable")
     return [int(i) for i in order[:m]]

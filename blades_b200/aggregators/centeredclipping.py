@@ -36,6 +36,17 @@ class Centeredclipping(_BaseAggregator):
 
     def aggregate(self, matrix):
         n, d = matrix.n_rows, matrix.n_cols
+        if n + 1 <= 512:
+            m = (self.momentum.to(matrix.device) if self.momentum is not None
+                 else torch.zeros(d, device=matrix.device, dtype=torch.float32))        # m_0 = 0
+            dg = matrix.gram_device(extra=m)
+            if dg is not None:
+                # clipping iterations on the device (csrc/cuda/gram_solve.cu); the last coefficient weighs m itself
+                from ..ops import gram_solve
+                c = gram_solve.centered_clip_coeffs(dg, self.tau, self.n_iter)
+                new_m = matrix.combine(c, extra=m)
+                self.momentum = new_m.detach().clone()
+                return new_m
         if self.momentum is None:
             # m = 0: Gram row/col of zeros, no need to touch the device for it
             G = matrix.gram()

@@ -37,18 +37,35 @@ class Geomed(_BaseAggregator):
         self.eps = eps
         self.ftol = ftol
         self.compat = compat
-        self.last_iterations = 0
+        self._iters = 0            # int, or a 1-element device tensor written by the on-device solver
 
     def _geometric_median_objective(self, median, points, alphas):
         """``sum_i alpha_i * ||median - p_i||`` (reference geomed.py:61-62; the solver itself works on the Gram matrix)."""
         return sum(float(a) * torch.linalg.norm(median - p) for a, p in zip(alphas, points))
 
+    @property
+    def last_iterations(self) -> int:
+        """Weiszfeld iterations of the last call (reading it after a device solve synchronises on that kernel)."""
+        if torch.is_tensor(self._iters):
+            self._iters = int(self._iters.item())
+        return self._iters
+
+    @last_iterations.setter
+    def last_iterations(self, v) -> None:
+        self._iters = v
+
     def weights_from_gram(self, G: np.ndarray, alphas=None) -> np.ndarray:
-        w, self.last_iterations = gops.weiszfeld_weights(
+        w, self._iters = gops.weiszfeld_weights(
             G, alphas, self.maxiter, self.eps, self.ftol, compounding=self.compat)
         return w
 
     def aggregate(self, matrix, weights=None):
+        dg = matrix.gram_device()
+        if dg is not None:
+            # Weiszfeld iterations on the device (csrc/cuda/gram_solve.cu): no D2H copy of G, no host sync
+            from ..ops import gram_solve
+            w, self._iters = gram_solve.weiszfeld_weights(dg, weights, self.maxiter, self.eps, self.ftol, self.compat)
+            return matrix.combine(w)
         return matrix.combine(self.weights_from_gram(matrix.gram(), weights))
 
     def __call__(self, inputs, weights=None):

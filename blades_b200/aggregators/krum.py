@@ -49,6 +49,14 @@ class Krum(_BaseAggregator):
         return gops.multi_krum_select(gops.sq_dists(G), self.f, self.m, n, squared_twice=self.compat)
 
     def aggregate(self, matrix):
+        dg = matrix.gram_device()
+        if dg is not None:
+            # scoring + selection on the device (csrc/cuda/gram_solve.cu): Gram -> weights -> combine without a host sync
+            from ..ops import gram_solve
+            n = dg.n if self.n is None else min(self.n, dg.n)
+            gops.check_krum_args(n, self.f, self.m)
+            value = 1.0 if self.compat else 1.0 / self.m
+            return matrix.combine(gram_solve.krum_weights(dg, n, self.f, self.m, self.compat, value))
         chosen = self.select(matrix.gram())
         w = np.zeros(matrix.n_rows)
         w[chosen] = 1.0 if self.compat else 1.0 / len(chosen)

@@ -4,7 +4,9 @@ replica of every trainer shard.
 One symmetric allocation per rank (``torch.distributed._symmetric_memory``: CUDA VMM + IPC handle
 exchange; NVLS multicast object when the fabric supports it), laid out identically everywhere:
 
-    [ U_g : nmax rows x ld floats ][ agg : ld ][ theta : ld ]
+    [ U_g : nmax rows x ld floats ][ agg : ld ][ theta : ld ][ scratch : 512 x 512 ]
+
+(``scratch`` holds the N x N Gram partials that are summed inside the NVSwitch, ``reduce_scratch``)
 
 so every kernel can address any peer's rows/agg/theta as ``peer_base[r] + same offset``.  ``ld`` is
 ``d`` rounded up to 64 floats: rows are 256 B aligned for 16 B vector loads and TMA.
@@ -16,12 +18,15 @@ enqueued on the current stream -- no host round trip).  Protocol per round:
 """
 from __future__ import annotations
 
+import os
 from typing import List, Sequence
 
 import torch
 import torch.distributed as dist
 
 __all__ = ["SymmetricUpdates", "round_up", "coordinate_shards"]
+
+SCRATCH_FLOATS = 512 * 512          # one padded N x N Gram (N <= 512)
 
 
 def round_up(x: int, m: int) -> int:
@@ -46,7 +51,8 @@ class SymmetricUpdates:
         self.nmax = max(self.shard_sizes)
         self.n_local = self.shard_sizes[world.rank]
         self.n_total = sum(self.shard_sizes)
-        total = self.nmax * self.ld + 2 * self.ld
+        self.scratch_floats = SCRATCH_FLOATS
+        total = self.nmax * self.ld + 2 * self.ld + self.scratch_floats
         self.buf = symm_mem.empty((total,), dtype=torch.float32, device=world.device)
         self.buf.zero_()
         self.handle = symm_mem.rendezvous(self.buf, dist.group.WORLD)
@@ -57,7 +63,11 @@ class SymmetricUpdates:
         self.local = self.local_full[: self.n_local, :d]
         self.agg = self.buf[self.off_agg: self.off_agg + d]
         self.theta = self.buf[self.off_theta: self.off_theta + d]
+        self.off_scratch = self.off_theta + self.ld
+        self.scratch = self.buf[self.off_scratch: self.off_scratch + self.scratch_floats]
         self.multicast_ptr = int(self.handle.multicast_ptr) if getattr(self.handle, "multicast_ptr", 0) else 0
+        if os.environ.get("BLADES_MULTIMEM", "1") == "0":       # A/B switch: per-peer stores / P2P reduction
+            self.multicast_ptr = 0
         # global row -> (rank, local row)
         self.row_owner = []
         for r, k in enumerate(self.shard_sizes):
@@ -78,6 +88,26 @@ class SymmetricUpdates:
     def theta_ptrs(self) -> List[int]:
         return [b + self.off_theta * 4 for b in self.base_ptrs]
 
+    def mc_agg_ptr(self) -> int:
+        """NVLS multicast address of ``agg`` (0 when the fabric has no multicast object)."""
+        return self.multicast_ptr + self.off_agg * 4 if self.multicast_ptr else 0
+
+    def mc_theta_ptr(self) -> int:
+        return self.multicast_ptr + self.off_theta * 4 if self.multicast_ptr else 0
+
+    def reduce_scratch(self, count: int) -> None:
+        """Sum the first ``count`` floats of ``scratch`` over all ranks, result in every replica: one two-shot
+        kernel per rank (``multimem.ld_reduce`` + ``multimem.st`` through the switch, or peer loads/stores), bracketed
+        by the device barrier.  Replaces the NCCL all-reduce of the Gram partials."""
+        from ..ops import nvls
+        count = round_up(count, 4)
+        assert count <= self.scratch_floats
+        self.barrier()
+        nvls.allreduce([b + self.off_scratch * 4 for b in self.base_ptrs],
+                       self.multicast_ptr + self.off_scratch * 4 if self.multicast_ptr else 0,
+                       count, self.world.rank, self.world.size, self.world.device)
+        self.barrier()
+
     def block_descs(self):
         """(base_ptr, ld, rows) of every rank's row block, in global row order."""
         return [(self.base_ptrs[r], self.ld, k) for r, k in enumerate(self.shard_sizes) if k > 0]
@@ -86,5 +116,5 @@ class SymmetricUpdates:
     def my_cols(self):
         return self.col_ranges[self.world.rank]
 
-    def barrier(self) -> None:
-        self.handle.barrier(channel=0)
+    def barrier(self, channel: int = 0) -> None:
+        self.handle.barrier(channel=channel)

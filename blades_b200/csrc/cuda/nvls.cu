@@ -1,0 +1,54 @@
+// In-fabric all-reduce of a small symmetric buffer -- the cross-GPU sum of the Gram partials (reference krum.py:85-90
+// computes its pairwise distances on the driver from the gathered updates; here every GPU holds the partial Gram of
+// its coordinate range and the N x N sums meet inside the NVSwitch).
+//
+// Two-shot, one kernel: rank r owns the r-th slice of the buffer,
+//   NVLS:   v = multimem.ld_reduce.add.v4.f32 [mc + i]   (the switch sums the G replicas)
+//           multimem.st.v4.f32 [mc + i], v               (and replicates the sum into every GPU's copy)
+//   no multicast object: the slice is summed with plain 16 B peer loads and written with one 16 B store per peer.
+// The caller brackets the launch with the symmetric-memory device barrier (partials complete / sums landed).
+#include "common.cuh"
+
+struct NvlsReduceParams {
+    float* peers[BL_MAX_PEERS];    // replica base pointers (peer-mapped), used when mc == nullptr
+    float* mc;                     // multicast address of the same buffer (nullptr: P2P path)
+    long long count;               // floats, multiple of 4
+    int rank, world;
+};
+
+__global__ void __launch_bounds__(256)
+nvls_allreduce_kernel(const __grid_constant__ NvlsReduceParams p) {
+    const long long vecs = p.count / 4;
+    const long long per = (vecs + p.world - 1) / p.world;
+    const long long v0 = per * p.rank, v1 = min(vecs, v0 + per);
+    for (long long i = v0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < v1; i += (long long)gridDim.x * blockDim.x) {
+        if (p.mc) {
+            const float4 v = bl_mc_ld_reduce4(p.mc + 4 * i);
+            bl_mc_store4(p.mc + 4 * i, v);
+        } else {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int g = 0; g < BL_MAX_PEERS; ++g)
+                if (g < p.world) {
+                    const float4 x = bl_ld_volatile4(p.peers[g] + 4 * i);
+                    acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+                }
+#pragma unroll
+            for (int g = 0; g < BL_MAX_PEERS; ++g)
+                if (g < p.world) *reinterpret_cast<float4*>(p.peers[g] + 4 * i) = acc;
+        }
+    }
+}
+
+extern "C" int bl_nvls_allreduce(const NvlsReduceParams* p, void* stream) {
+    if (p->count <= 0) return 0;
+    if (p->count % 4 != 0 || p->world < 1 || p->world > BL_MAX_PEERS) return -1;
+    const long long per = (p->count / 4 + p->world - 1) / p->world;
+    unsigned grid = (unsigned)((per + 255) / 256);
+    if (grid > 148u * 4) grid = 148u * 4;
+    if (grid < 1) grid = 1;
+    nvls_allreduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int bl_sizeof_nvls_reduce_params() { return (int)sizeof(NvlsReduceParams); }

@@ -46,28 +46,62 @@ BL_CORE_FN float bl_virtual_value(const float (&a)[NP / 2], const float (&b)[NP 
     return mu - param * sqrtf(q / (fstat - 1.f));
 }
 
+// Sum of all NP values (four independent chains).  NaN / +-inf exactly when some value is non-finite (or the finite sum
+// overflows): the kernel's cue for the nan_to_num slow path; the mean of the attack statistics when every row is honest.
+template <int NP>
+BL_CORE_FN float bl_total(const float (&a)[NP / 2], const float (&b)[NP / 2]) {
+    constexpr int H = NP / 2;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+    for (int i = 0; i + 1 < H; i += 2) { t0 += a[i]; t1 += a[i + 1]; t2 += b[i]; t3 += b[i + 1]; }
+    if (H % 2) { t0 += a[H - 1]; t2 += b[H - 1]; }
+    return (t0 + t1) + (t2 + t3);
+}
+
+// bl_virtual_value when all NP rows are honest (n_stat == NP): no rank masks, the mean comes from the total.
+template <int NP>
+BL_CORE_FN float bl_virtual_value_all(const float (&a)[NP / 2], const float (&b)[NP / 2], float total, int kind, float param) {
+    constexpr int H = NP / 2;
+    const float mu = total / (float)NP;
+    if (kind != 1) return -param * mu;
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        const float da = a[i] - mu, db = b[i] - mu;
+        q0 = fmaf(da, da, q0);
+        q1 = fmaf(db, db, q1);
+    }
+    return mu - param * sqrtf((q0 + q1) / (float)(NP - 1));
+}
+
 // Trimmed mean of the NP real values (+ f copies of m), trimming Q = NP/4 from each end.  Requires f == 0 or f >= Q.
 // Destroys a and b (sorted in place).
-template <int NP>
+template <int NP, int MIX = 0>
 BL_CORE_FN float bl_trimmed_partition(float (&a)[NP / 2], float (&b)[NP / 2], float m, int f) {
     static_assert(NP % 8 == 0 && NP >= 8 && NP <= 128, "halves must be SortNet sizes (multiples of 4)");
     constexpr int H = NP / 2, Q = NP / 4;
-    SortNet<H>::run(a);
-    SortNet<H>::run(b);
-    float mid0 = 0.f, mid1 = 0.f, ext = 0.f;
-    const float use = f > 0 ? 1.f : 0.f;
+    SortNet<H>::template run<MIX>(a);
+    SortNet<H>::template run<MIX>(b);
+    float mid0 = 0.f, mid1 = 0.f, ext0 = 0.f, ext1 = 0.f;
+    if (f > 0) {                                               // uniform branch (kernel parameter)
 #pragma unroll
-    for (int i = 0; i < Q; ++i) {
-        const float x = a[i], y = b[Q - 1 - i];
-        mid0 += fmaxf(x, y);                                   // loser of the bottom split -> middle
-        ext = fmaf(use, fmaxf(fminf(x, y) - m, 0.f), ext);     // bottom-set member above m stays (as x - m + m)
-    }
+        for (int i = 0; i < Q; ++i) {
+            const float x = a[i], y = b[Q - 1 - i];
+            mid0 += fmaxf(x, y);                               // loser of the bottom split -> middle
+            ext0 += fmaxf(fminf(x, y), m) - m;                 // bottom-set member above m stays (as x - m + m)
+        }
 #pragma unroll
-    for (int i = 0; i < Q; ++i) {
-        const float x = a[Q + i], y = b[H - 1 - i];
-        mid1 += fminf(x, y);                                   // loser of the top split -> middle
-        ext = fmaf(use, fminf(fmaxf(x, y) - m, 0.f), ext);     // top-set member below m stays
+        for (int i = 0; i < Q; ++i) {
+            const float x = a[Q + i], y = b[H - 1 - i];
+            mid1 += fminf(x, y);                               // loser of the top split -> middle
+            ext1 += fminf(fmaxf(x, y), m) - m;                 // top-set member below m stays
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) mid0 += fmaxf(a[i], b[Q - 1 - i]);
+#pragma unroll
+        for (int i = 0; i < Q; ++i) mid1 += fminf(a[Q + i], b[H - 1 - i]);
     }
-    const float kept = (mid0 + mid1) + ext + (float)f * (f > 0 ? m : 0.f);
+    const float kept = (mid0 + mid1) + (ext0 + ext1) + (float)f * (f > 0 ? m : 0.f);
     return kept / (float)(NP + f - 2 * Q);
 }

@@ -424,13 +424,13 @@ def batched_loss(logits: torch.Tensor, target: torch.Tensor, n: int, clamp: torc
 
 
 def batched_step(model: nn.Module, sink: GradSink, x: torch.Tensor, y: torch.Tensor, n: int,
-                 clamp: torch.Tensor) -> torch.Tensor:
+                 clamp: torch.Tensor, progress=None) -> torch.Tensor:
     """One client-batched fedsgd step: fills ``sink`` with ``alpha * grad_c`` for the ``n`` clients whose samples are
     concatenated in ``x`` / ``y`` and returns the per-client mean losses.  The ResNet family runs the explicit
     all-own-kernels schedule (``engine/resnet_fused.py``) on B200; everything else the swapped-forward autograd pass."""
     from . import resnet_fused as rf
     if rf.supports(model, sink, x):
-        return rf.step(model, sink, x, y, n, clamp)
+        return rf.step(model, sink, x, y, n, clamp, progress)      # ``progress``: see resnet_fused.step
     with client_batched(model, sink, x.shape[0]):
         logits = model(x)
         if logits.is_cuda and logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1 \

@@ -208,10 +208,10 @@ def _forward(ps: _Pass, x: torch.Tensor):
     k, st, pd = as_int(mp.kernel_size), as_int(mp.stride), as_int(mp.padding)
     h, pool_idx = kf.maxpool_fwd(stem.y, k, st, pd)
     saved = []
-    for layer in (model.layer1, model.layer2, model.layer3, model.layer4):
+    for li, layer in enumerate((model.layer1, model.layer2, model.layer3, model.layer4)):
         for blk in layer:
             h, sv = _block_fwd(ps, blk, h)
-            saved.append(sv if ps.keep else None)
+            saved.append((li + 1, sv) if ps.keep else None)
     NB, Cf, Hf, Wf = h.shape
     feat = h.reshape(NB, Cf) if Hf * Wf == 1 else kf.avgpool_fwd(h)
     if Hf * Wf == 1:
@@ -229,9 +229,20 @@ def forward_logits(model: ResNet, x: torch.Tensor, n_groups: int) -> torch.Tenso
         return _forward(_Pass(model, None, n_groups, keep=False), x)[0]
 
 
-def step(model: ResNet, sink, x: torch.Tensor, y: torch.Tensor, n: int, clamp: torch.Tensor) -> torch.Tensor:
+def _final_from(sink, prefixes) -> int:
+    """Smallest flat offset of the parameters under the given module-name prefixes."""
+    return min(sp.offset for name, sp in sink.by_name.items() if name.startswith(prefixes))
+
+
+def step(model: ResNet, sink, x: torch.Tensor, y: torch.Tensor, n: int, clamp: torch.Tensor,
+         progress=None) -> torch.Tensor:
     """One fedsgd step of ``n`` clients (x: ``[n*B, Cin, H, W]`` in any layout, y: ``[n*B]`` int64): fills the rows of
-    ``sink.out`` with ``-lr * grad_c`` and returns the per-client mean losses."""
+    ``sink.out`` with ``-lr * grad_c`` and returns the per-client mean losses.
+
+    ``progress(lo)``: called during the backward pass each time a stage of the network is done, with the flat offset
+    ``lo`` from which on every update coordinate is final (the backward pass visits fc, layer4, ..., layer1, the stem,
+    and the flat vector stores them in the opposite order, so the finished part is always a suffix).  The round engine
+    uses it to start aggregating those coordinates on a side stream while the rest of the backward pass still runs."""
     ps = _Pass(model, sink, n)
     s = sink
     with torch.no_grad():
@@ -250,8 +261,13 @@ def step(model: ResNet, sink, x: torch.Tensor, y: torch.Tensor, n: int, clamp: t
         g = gfeat.view(NB, Cf, 1, 1) if Hf * Wf == 1 else kf.avgpool_bwd(gfeat, (Hf, Wf))
         if Hf * Wf == 1:
             g = g.contiguous(memory_format=torch.channels_last)      # no-op for 1x1 maps (both layouts coincide)
-        for sv in reversed(saved):
+        ordered = progress is not None and _final_from(s, ("fc.",)) > _final_from(s, ("layer4.",)) > \
+            _final_from(s, ("layer3.",)) > _final_from(s, ("layer2.",)) > _final_from(s, ("layer1.",)) > 0
+        for i in range(len(saved) - 1, -1, -1):
+            li, sv = saved[i]
             g = _block_bwd(ps, sv, g)
+            if ordered and (i == 0 or saved[i - 1][0] != li):        # first block of stage li done: the stage is final
+                progress(_final_from(s, (f"layer{li}.",)))
         gy = kf.maxpool_bwd(g, pool_idx, tuple(stem.y.shape[2:]), k, st, pd)
         gc = ps.bn_bwd(stem, gy, want_masked=False)
         ps.wgrad(stem, gc)

@@ -90,6 +90,48 @@ class PhaseTimer:
         return out
 
 
+class _AggPipeline:
+    """Pipelined aggregation inside the whole-round graph.  ``progress(lo)`` (called by the backward pass) says that
+    every update coordinate ``>= lo`` is final; once enough of them have accumulated, the aggregation of that window
+    (pre-barrier across the GPUs on the window's own channel, fused attack + select / combine + server step over the
+    rank's share of the window) is enqueued on a low-priority side stream that forks off the training stream, and
+    joins it again after the last window.  Per-coordinate arithmetic is unchanged, so the result is bit-identical to
+    the unpipelined round; what changes is that the pull over NVLink and the selection network overlap the rest of
+    the backward pass instead of following it (reference: gather + aggregate strictly after training,
+    simulator.py:235-245)."""
+
+    MIN_FRACTION = 0.04          # smaller windows wait for the next stage
+
+    def __init__(self, eng: "RoundEngine", aggregate_fn):
+        self.eng, self.fn = eng, aggregate_fn
+        self.hi = eng.d
+        self.k = 0
+        self.windows = []
+        self.out = None if eng.symm is not None else torch.empty(eng.d, device=eng.device, dtype=torch.float32)
+        self.agg = None
+
+    def _launch(self, lo: int, hi: int, last: bool) -> None:
+        main = torch.cuda.current_stream(self.eng.device)
+        side = self.eng._agg_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self.agg = self.fn(window=(lo, hi), chunk=self.k, last=last, out=self.out)
+        self.windows.append((lo, hi))
+        self.k += 1
+        self.hi = lo
+
+    def progress(self, lo: int) -> None:
+        lo = (int(lo) + 127) // 128 * 128              # whole 512 B row segments per window (round up: coordinates below ``lo`` are not final yet)
+        if lo <= 0 or (self.hi - lo) < self.MIN_FRACTION * self.eng.d or self.k >= 6:
+            return
+        self._launch(lo, self.hi, False)
+
+    def finish(self):
+        self._launch(0, self.hi, True)
+        torch.cuda.current_stream(self.eng.device).wait_stream(self.eng._agg_stream)
+        return self.agg
+
+
 def _overrides(obj, name: str, base=BladesClient) -> bool:
     return getattr(type(obj), name) is not getattr(base, name)
 
@@ -625,9 +667,17 @@ class RoundEngine:
             graph = torch.cuda.CUDAGraph()
             before = _loader.LAUNCHES
             try:
-                with torch.cuda.graph(graph, capture_error_mode=_CAPTURE_MODE):
-                    losses = self._batched_step(rows, lr, sx, sy)
-                    agg = aggregate_fn()
+                pipe = _AggPipeline(self, aggregate_fn) if self._pipeline_enabled() else None
+                with torch.cuda.graph(graph, stream=self._capture_stream(), capture_error_mode=_CAPTURE_MODE):
+                    if pipe is None:
+                        losses = self._batched_step(rows, lr, sx, sy)
+                        agg = aggregate_fn()
+                    else:
+                        # aggregation of the coordinates whose backward pass is done starts on a side stream while
+                        # the rest of the backward pass still runs (fork / join inside the captured graph)
+                        losses = self._batched_step(rows, lr, sx, sy, progress=pipe.progress)
+                        agg = pipe.finish()
+                        st["chunks"] = pipe.windows
                 mat = matrix_fn()
                 ok = mat is not None and mat.step_applied
             except Exception as e:     # capture is an optimisation: fall back to eager rounds, but say so
@@ -664,8 +714,22 @@ class RoundEngine:
                 [float(self.clients[self.local_idx[r]].loss_clamp) for r in rows], device=self.device)
         return t
 
-    def _batched_step(self, rows: List[int], lr: float, X: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-        """X: [n, 1, B, ...], y: [n, 1, B] on the device (may be modified in place by client hooks)."""
+    def _pipeline_enabled(self) -> bool:
+        import os
+        return os.environ.get("BLADES_AGG_PIPELINE", "1") != "0"
+
+    def _capture_stream(self) -> torch.cuda.Stream:
+        """Stream the whole-round graph is captured on: one priority level above the aggregation side stream, so the
+        block scheduler serves the (latency-bound) training chain first and the streaming aggregation kernels fill
+        the SMs it leaves idle."""
+        if getattr(self, "_cap_stream", None) is None:
+            self._cap_stream = torch.cuda.Stream(device=self.device, priority=-1)
+            self._agg_stream = torch.cuda.Stream(device=self.device, priority=0)
+        return self._cap_stream
+
+    def _batched_step(self, rows: List[int], lr: float, X: torch.Tensor, y: torch.Tensor, progress=None) -> torch.Tensor:
+        """X: [n, 1, B, ...], y: [n, 1, B] on the device (may be modified in place by client hooks).
+        ``progress``: see ``resnet_fused.step`` (ignored when rows need a post-pass: sign flips, scattered rows)."""
         model = self.server.get_model()
         n = len(rows)
         X = X[:, 0]
@@ -686,7 +750,10 @@ class RoundEngine:
         out = self.U[rows[0]: rows[0] + n] if contiguous_rows else torch.empty(n, self.d, device=self.device)
         sink = cb.GradSink(out, self.gflat.specs, n, alpha=-lr)
         model.train()
-        per_client = cb.batched_step(model, sink, X.reshape((n * B,) + tuple(X.shape[2:])), y.reshape(-1), n, clamp)
+        if signs or not contiguous_rows:
+            progress = None
+        per_client = cb.batched_step(model, sink, X.reshape((n * B,) + tuple(X.shape[2:])), y.reshape(-1), n, clamp,
+                                     progress)
         missing = [s.name for s in self.gflat.specs if s.name not in sink.written]
         for name in missing:       # parameters unused in the forward pass: zero update
             sink.view(name).zero_()

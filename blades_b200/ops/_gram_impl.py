@@ -53,6 +53,17 @@ def split_blocks(ptr: int, ld: int, rows: int, max_rows: int = 256) -> List[Tupl
 
 
 def gram_tcgen05(lib, data: torch.Tensor, extra: Optional[torch.Tensor], precision: str) -> Optional[torch.Tensor]:
+    r = gram_padded(lib, data, extra, precision)
+    if r is None:
+        return None
+    out, idx = r
+    idx_t = torch.tensor(idx, device=data.device)
+    G = out[idx_t][:, idx_t]
+    return 0.5 * (G + G.T)
+
+
+def gram_padded(lib, data: torch.Tensor, extra: Optional[torch.Tensor], precision: str):
+    """(padded accumulators ``[tile_rows, ld]``, logical -> padded row list) or None when the kernel does not apply."""
     n, d = data.shape
     if data.stride(1) != 1 or data.stride(0) % 4 != 0 or data.data_ptr() % 16 != 0:
         return None
@@ -79,6 +90,4 @@ def gram_tcgen05(lib, data: torch.Tensor, extra: Optional[torch.Tensor], precisi
     idx = []
     for (ptr, ld, rows), s in zip(blocks, starts):
         idx += list(range(s, s + rows))
-    idx_t = torch.tensor(idx, device=data.device)
-    G = out[idx_t][:, idx_t]
-    return 0.5 * (G + G.T)
+    return out, idx

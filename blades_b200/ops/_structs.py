@@ -8,7 +8,8 @@ fptr = C.c_void_p
 
 class Epilogue(C.Structure):
     _fields_ = [("out", fptr * MAX_PEERS), ("theta", fptr * MAX_PEERS), ("theta_src", fptr),
-                ("lr", C.c_float), ("n_out", C.c_int), ("n_theta", C.c_int)]
+                ("lr", C.c_float), ("n_out", C.c_int), ("n_theta", C.c_int),
+                ("mc_out", fptr), ("mc_theta", fptr)]         # NVLS multicast addresses (0: one store per peer)
 
 
 class SelectParams(C.Structure):
@@ -25,7 +26,8 @@ class SelectLargeParams(C.Structure):
 
 class CombineParams(C.Structure):
     _fields_ = [("rows", fptr * (MAX_ROWS + 1)), ("w", C.c_float * (MAX_ROWS + 1)), ("n_rows", C.c_int),
-                ("c0", C.c_longlong), ("c1", C.c_longlong), ("ep", Epilogue)]
+                ("c0", C.c_longlong), ("c1", C.c_longlong), ("ep", Epilogue), ("ep_vec", C.c_int),
+                ("w_dev", fptr)]          # device-resident weights (on-device Gram solvers); overrides w
 
 
 class AttackRowParams(C.Structure):

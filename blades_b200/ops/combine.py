@@ -21,9 +21,21 @@ def _num_sms(device) -> int:
     return _SMS[idx]
 
 
-def launch_combine(rows: Sequence[int], weights: Sequence[float], c0: int, c1: int,
+def launch_combine(rows: Sequence[int], weights, c0: int, c1: int,
                    ep: _structs.Epilogue, device=None) -> None:
+    """``weights``: a sequence of floats, or a CUDA fp32 tensor with one weight per row (written by the on-device Gram
+    solvers): then the kernel reads the weights from device memory and skips zero-weight rows itself."""
     lib = _loader.cuda_lib()
+    if torch.is_tensor(weights):
+        assert weights.is_cuda and weights.dtype == torch.float32 and weights.is_contiguous()
+        assert weights.numel() == len(rows) <= _structs.MAX_ROWS + 1
+        p = _structs.CombineParams()
+        for i, r in enumerate(rows):
+            p.rows[i] = r
+        p.n_rows, p.c0, p.c1, p.ep, p.w_dev = len(rows), c0, c1, ep, weights.data_ptr()
+        _loader.check(lib.bl_row_combine(C.byref(p), _num_sms(device), _loader.stream_ptr(device)), "row_combine")
+        _loader.count_launch()
+        return
     keep = [(r, float(w)) for r, w in zip(rows, weights) if float(w) != 0.0]
     if not keep:                      # all-zero weights: still must produce zeros
         keep = [(rows[0], 0.0)]

@@ -1,0 +1,29 @@
+"""Launcher of the in-fabric all-reduce (csrc/cuda/nvls.cu): two-shot sum of a symmetric buffer over all ranks,
+``multimem.ld_reduce`` + ``multimem.st`` through the NVSwitch when a multicast address is given, peer loads/stores
+otherwise."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+from . import _loader, _structs
+
+__all__ = ["allreduce"]
+
+
+class NvlsReduceParams(C.Structure):
+    _fields_ = [("peers", C.c_void_p * _structs.MAX_PEERS), ("mc", C.c_void_p), ("count", C.c_longlong),
+                ("rank", C.c_int), ("world", C.c_int)]
+
+
+def allreduce(peer_ptrs: Sequence[int], mc_ptr: int, count: int, rank: int, world: int, device=None) -> None:
+    lib = _loader.cuda_lib()
+    assert lib.bl_sizeof_nvls_reduce_params() == C.sizeof(NvlsReduceParams)
+    assert len(peer_ptrs) == world <= _structs.MAX_PEERS and count % 4 == 0
+    p = NvlsReduceParams()
+    for i, b in enumerate(peer_ptrs):
+        p.peers[i] = b
+    p.mc = mc_ptr or None
+    p.count, p.rank, p.world = count, rank, world
+    _loader.check(lib.bl_nvls_allreduce(C.byref(p), _loader.stream_ptr(device)), "nvls_allreduce")
+    _loader.count_launch()

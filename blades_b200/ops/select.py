@@ -24,8 +24,12 @@ def row_pointers(data: torch.Tensor, rows: Optional[Sequence[int]] = None) -> Li
 
 
 def make_epilogue(outs: Sequence[int], thetas: Sequence[int] = (), theta_src: int = 0,
-                  lr: float = 0.0) -> _structs.Epilogue:
+                  lr: float = 0.0, mc_out: int = 0, mc_theta: int = 0) -> _structs.Epilogue:
+    """``mc_out`` / ``mc_theta``: NVLS multicast addresses of the replicated ``agg`` / ``theta`` (one ``multimem.st``
+    per value instead of one store per peer pointer); 0 keeps the per-peer stores."""
     ep = _structs.Epilogue()
+    ep.mc_out = mc_out or None
+    ep.mc_theta = (mc_theta or None) if len(thetas) else None
     assert len(outs) <= _structs.MAX_PEERS and len(thetas) <= _structs.MAX_PEERS
     for i, p in enumerate(outs):
         ep.out[i] = p

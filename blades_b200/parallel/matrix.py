@@ -77,6 +77,16 @@ class UpdateMatrix:
     #: (lr,) -> the final primitive also applies ``theta += lr * agg`` on every replica (K8 fusion)
     server_step = None
     step_applied = False
+    #: pipelined aggregation (engine/round.py): this matrix object only covers coordinates ``[window[0], window[1])``
+    #: -- chunk number ``chunk`` of the round, ``last_chunk`` closes it.  Coordinate-wise primitives (mean / combine,
+    #: trimmed mean, median, virtual-row materialisation) honour it; ``out_buffer`` is the round's shared result vector.
+    window = None
+    chunk = 0
+    last_chunk = True
+    out_buffer = None
+
+    def _cols(self):
+        return (0, self.n_cols) if self.window is None else (int(self.window[0]), int(self.window[1]))
 
     # coordinate-wise -----------------------------------------------------------
     def mean(self) -> torch.Tensor:
@@ -90,6 +100,11 @@ class UpdateMatrix:
     def median(self) -> torch.Tensor: raise NotImplementedError
     # geometry ------------------------------------------------------------------
     def gram(self, extra: Optional[torch.Tensor] = None) -> np.ndarray: raise NotImplementedError
+
+    def gram_device(self, extra: Optional[torch.Tensor] = None):
+        """The Gram matrix left ON THE DEVICE (``ops.gram_solve.DeviceGram``) for the on-device solvers, or ``None``
+        when this matrix has no kernel path (CPU oracle): callers then fall back to ``gram()`` + the host solvers."""
+        return None
     # escape hatch ----------------------------------------------------------------
     def rows(self) -> torch.Tensor: raise NotImplementedError
 
@@ -135,8 +150,9 @@ class LocalMatrix(UpdateMatrix):
                 from ..ops import attack as _a, select as _s
                 byz = set(v.byzantine)
                 honest = [i for i in range(self.n_rows) if i not in byz]
+                c0, c1 = self._cols()
                 _a.attack_rows(_s.row_pointers(self.data, honest), _s.row_pointers(self.data, list(v.replaced)),
-                               v.kind, v.param, 0, self.n_cols, self.data.device)
+                               v.kind, v.param, c0, c1, self.data.device)
             else:
                 val = v.value(self._honest())
                 self.data[list(v.replaced)] = val
@@ -147,6 +163,11 @@ class LocalMatrix(UpdateMatrix):
         return self.materialize_virtual()
 
     # -- primitives -----------------------------------------------------------------
+    def _out(self, device) -> torch.Tensor:
+        if self.out_buffer is not None:
+            return self.out_buffer
+        return torch.empty(self.n_cols, device=device, dtype=torch.float32)
+
     def _epilogue(self, out: torch.Tensor):
         from ..ops import select as _s
         if self.server_step is not None and self.theta is not None:
@@ -156,6 +177,19 @@ class LocalMatrix(UpdateMatrix):
         return _s.make_epilogue([out.data_ptr()])
 
     def combine(self, weights, extra: Optional[torch.Tensor] = None, extra_weight: float = 0.0) -> torch.Tensor:
+        if self.use_kernels and torch.is_tensor(weights) and weights.is_cuda:
+            # device-resident weights (on-device Gram solvers); with ``extra`` the last weight belongs to it
+            from ..ops import combine as _k, select as _s
+            data = self.rows()
+            rows = _s.row_pointers(data)
+            keep = None
+            if extra is not None:
+                keep = extra.to(data.device, torch.float32).contiguous()
+                rows = rows + [keep.data_ptr()]
+            out = self._out(data.device)
+            c0, c1 = self._cols()
+            _k.launch_combine(rows, weights.to(torch.float32).contiguous(), c0, c1, self._epilogue(out), data.device)
+            return out
         w = torch.as_tensor(np.asarray(weights, dtype=np.float64) if not torch.is_tensor(weights) else weights)
         if self.use_kernels:
             from ..ops import combine as _k, select as _s
@@ -165,8 +199,9 @@ class LocalMatrix(UpdateMatrix):
             if extra is not None and extra_weight != 0.0:
                 extra = extra.contiguous()
                 rows, wl = rows + [extra.data_ptr()], wl + [float(extra_weight)]
-            out = torch.empty(self.n_cols, device=data.device, dtype=torch.float32)
-            _k.launch_combine(rows, wl, 0, self.n_cols, self._epilogue(out), data.device)
+            out = self._out(data.device)
+            c0, c1 = self._cols()
+            _k.launch_combine(rows, wl, c0, c1, self._epilogue(out), data.device)
             return out
         data = self.rows()
         res = (w.to(data.device, torch.float64)[:, None] * data.double()).sum(0)
@@ -194,15 +229,16 @@ class LocalMatrix(UpdateMatrix):
     def _select_kernel(self, mode: int, b: int) -> torch.Tensor:
         from ..ops import select as _s
         data, v, n = self.data, self.virtual, self.n_rows
-        out = torch.empty(self.n_cols, device=data.device, dtype=torch.float32)
+        out = self._out(data.device)
+        c0, c1 = self._cols()
         if v is not None and v.count:
             byz, rep = set(v.byzantine), set(v.replaced)
             stat = _s.row_pointers(data, [i for i in range(n) if i not in byz])
             other = _s.row_pointers(data, [i for i in range(n) if i in byz and i not in rep])
-            _s.launch_select(stat, other, v.count, v.kind, v.param, mode, b, 0, self.n_cols,
+            _s.launch_select(stat, other, v.count, v.kind, v.param, mode, b, c0, c1,
                              self._epilogue(out), data.device)
         else:
-            _s.launch_select(_s.row_pointers(data), [], 0, None, 0.0, mode, b, 0, self.n_cols,
+            _s.launch_select(_s.row_pointers(data), [], 0, None, 0.0, mode, b, c0, c1,
                              self._epilogue(out), data.device)
         return out
 
@@ -224,6 +260,25 @@ class LocalMatrix(UpdateMatrix):
         full = data if extra is None else torch.cat([data, extra], 0)
         full = full.double()
         return (full @ full.T).cpu().numpy()
+
+
+def _local_gram_device(self, extra: Optional[torch.Tensor] = None):
+    if not self.use_kernels:
+        return None
+    from ..ops import _gram_impl, _loader, gram as _k, gram_solve
+    if not gram_solve.enabled() or _k.PRECISION == "fp32":
+        return None
+    data = self.rows()
+    if extra is not None:
+        extra = extra.reshape(-1, self.n_cols).to(data.device, data.dtype)
+    r = _gram_impl.gram_padded(_loader.cuda_lib(), data, extra, _k.PRECISION)
+    if r is None:
+        return None
+    out, idx = r
+    return gram_solve.DeviceGram(out, torch.tensor(idx, dtype=torch.int32, device=data.device), len(idx))
+
+
+LocalMatrix.gram_device = _local_gram_device
 
 
 def as_matrix(inputs, virtual: Optional[VirtualRows] = None) -> UpdateMatrix:

@@ -36,20 +36,37 @@ class ShardedMatrix(UpdateMatrix):
         self._synced = False
 
     # ------------------------------------------------------------------ helpers
+    def _cols(self):
+        """This rank's coordinate range: its shard of the whole vector, or -- pipelined aggregation -- its shard of the
+        window this matrix object covers (every window is split evenly over the ranks)."""
+        if self.window is None:
+            return self.symm.my_cols
+        from ..comm.symm import coordinate_shards
+        lo, hi = int(self.window[0]), int(self.window[1])
+        c0, c1 = coordinate_shards(hi - lo, self.symm.world.size)[self.symm.world.rank]
+        return lo + c0, lo + c1
+
+    def _barrier(self):
+        # chunks of a pipelined round run on a side stream while the main stream still trains: their flag exchanges
+        # use their own signal-pad channel (1 + chunk); channel 0 closes the round
+        self.symm.barrier(0 if self.window is None else 1 + self.chunk)
+
     def _pre(self):
-        if not self._synced:             # all ranks finished writing their rows
-            self.symm.barrier()
+        if not self._synced:             # all ranks finished writing their rows (of this window)
+            self._barrier()
             self._synced = True
 
     def _epilogue(self, final: bool):
         s = self.symm
         if final and self.server_step is not None:
             self.step_applied = True
-            return k_select.make_epilogue(s.agg_ptrs(), s.theta_ptrs(), s.theta.data_ptr(), float(self.server_step[0]))
-        return k_select.make_epilogue(s.agg_ptrs())
+            return k_select.make_epilogue(s.agg_ptrs(), s.theta_ptrs(), s.theta.data_ptr(), float(self.server_step[0]),
+                                          mc_out=s.mc_agg_ptr(), mc_theta=s.mc_theta_ptr())
+        return k_select.make_epilogue(s.agg_ptrs(), mc_out=s.mc_agg_ptr())
 
     def _finish(self) -> torch.Tensor:
-        self.symm.barrier()              # every shard of agg/theta has landed everywhere
+        if self.window is None or self.last_chunk:
+            self.symm.barrier()          # every shard of agg/theta has landed everywhere
         return self.symm.agg
 
     def materialize_virtual(self):
@@ -59,17 +76,17 @@ class ShardedMatrix(UpdateMatrix):
             s = self.symm
             byz = set(v.byzantine)
             honest = [i for i in range(self.n_rows) if i not in byz]
-            c0, c1 = s.my_cols
+            c0, c1 = self._cols()
             k_attack.attack_rows(s.row_ptrs(honest), s.row_ptrs(list(v.replaced)), v.kind, v.param, c0, c1,
                                  self.device)
             self.virtual = None
-            s.barrier()
+            self._barrier()
 
     # ------------------------------------------------------------------ primitives
     def _select(self, mode: int, b: int) -> torch.Tensor:
         self._pre()
         s = self.symm
-        c0, c1 = s.my_cols
+        c0, c1 = self._cols()
         v = self.virtual
         if v is not None and v.count:
             byz, rep = set(v.byzantine), set(v.replaced)
@@ -94,16 +111,39 @@ class ShardedMatrix(UpdateMatrix):
         self.materialize_virtual()
         self._pre()
         s = self.symm
+        if torch.is_tensor(weights) and weights.is_cuda:
+            # device-resident weights (on-device Gram solvers): no host copy; with ``extra`` the last weight is its
+            rows = s.row_ptrs(range(self.n_rows))
+            if extra is not None:
+                self._keep = extra.to(self.device, torch.float32).contiguous()
+                rows = rows + [self._keep.data_ptr()]
+            c0, c1 = self._cols()
+            k_combine.launch_combine(rows, weights.to(torch.float32).contiguous(), c0, c1, self._epilogue(True), self.device)
+            return self._finish()
         w = [float(x) for x in (weights.tolist() if hasattr(weights, "tolist") else weights)]
         rows = s.row_ptrs(range(self.n_rows))
         if extra is not None and extra_weight != 0.0:
             rows = rows + [extra.contiguous().data_ptr()]
             w = w + [float(extra_weight)]
-        c0, c1 = s.my_cols
+        c0, c1 = self._cols()
         k_combine.launch_combine(rows, w, c0, c1, self._epilogue(True), self.device)
         return self._finish()
 
     def gram(self, extra: Optional[torch.Tensor] = None) -> np.ndarray:
+        out, idx = self._gram_scratch(extra)
+        idx_t = torch.tensor(idx, device=self.device)
+        G = out[idx_t][:, idx_t]
+        return (0.5 * (G + G.T)).double().cpu().numpy()
+
+    def gram_device(self, extra: Optional[torch.Tensor] = None):
+        from ..ops import gram_solve
+        if not gram_solve.enabled():
+            return None
+        out, idx = self._gram_scratch(extra)
+        return gram_solve.DeviceGram(out, torch.tensor(idx, dtype=torch.int32, device=self.device), len(idx))
+
+    def _gram_scratch(self, extra: Optional[torch.Tensor] = None):
+        """Summed Gram accumulators in every rank's symmetric scratch region + the logical -> padded row list."""
         from ..ops import _gram_impl, gram as k_gram
         self.materialize_virtual()
         self._pre()
@@ -122,16 +162,19 @@ class ShardedMatrix(UpdateMatrix):
         assert total_pad <= 512 and len(blocks) <= 9, "too many rows/blocks for one Gram pass"
         tile_rows = (total_pad + 127) // 128 * 128
         ldg = (total_pad + 31) // 32 * 32
-        out = torch.zeros(tile_rows, ldg, device=self.device, dtype=torch.float32)
+        # partials accumulate in this rank's replica of the symmetric scratch region; the cross-GPU sum happens in the
+        # NVSwitch (multimem.ld_reduce / multimem.st, csrc/cuda/nvls.cu) -- no NCCL call on the aggregation path
+        out = s.scratch[: tile_rows * ldg].view(tile_rows, ldg)
+        out.zero_()
         c0, c1 = s.my_cols
         starts = _gram_impl.launch_gram(blocks, self.n_cols, c0, c1, out, k_gram.PRECISION == "tf32x3", self.device)
-        dist.all_reduce(out)             # N x N partials (<= 1 MB): NCCL is plumbing here
+        if starts is None:               # 3xTF32 staging does not fit for this row count: plain tf32
+            starts = _gram_impl.launch_gram(blocks, self.n_cols, c0, c1, out, False, self.device)
+        s.reduce_scratch(tile_rows * ldg)
         idx = []
         for (_, _, rows), st in zip(blocks, starts):
             idx += list(range(st, st + rows))
-        idx_t = torch.tensor(idx, device=self.device)
-        G = out[idx_t][:, idx_t]
-        return (0.5 * (G + G.T)).double().cpu().numpy()
+        return out, idx
 
     def rows(self) -> torch.Tensor:
         self.materialize_virtual()

@@ -241,7 +241,9 @@ class Simulator(object):
         return out
 
     # ------------------------------------------------------------------ one round
-    def _aggregate(self, virtual: Optional[VirtualRows]):
+    def _aggregate(self, virtual: Optional[VirtualRows], window=None, chunk: int = 0, last: bool = True, out=None):
+        """``window`` / ``chunk`` / ``last`` / ``out``: pipelined aggregation (``RoundEngine.static_round``) -- aggregate
+        only the coordinates ``[window[0], window[1])`` into the round's shared result vector."""
         eng = self.engine
         agg = self.aggregator
         from .aggregators.base import _BaseAggregator
@@ -253,6 +255,8 @@ class Simulator(object):
         if isinstance(agg, _BaseAggregator):
             from .aggregators.fltrust import Fltrust
             matrix = eng.make_matrix(virtual)
+            if window is not None:
+                matrix.window, matrix.chunk, matrix.last_chunk, matrix.out_buffer = window, chunk, last, out
             if self._opts["fuse_server_step"] and getattr(agg, "fusable_final", False) \
                     and self.server._flat_fast_path_ok() and getattr(matrix, "use_kernels", True):
                 matrix.server_step = (self.server.current_lr(),)
@@ -278,7 +282,7 @@ class Simulator(object):
             # whole round (train -> barrier -> fused attack+aggregate+server step -> barrier) as ONE CUDA
             # graph replay: no per-round Python/launch overhead (matters most when G GPUs split the work)
             virtual = self._cached_virtual()
-            if eng.static_round(lr, lambda: self._aggregate(virtual), lambda: self._last_matrix):
+            if eng.static_round(lr, lambda **kw: self._aggregate(virtual, **kw), lambda: self._last_matrix):
                 self.last_aggregate = eng.static_aggregate
                 return
         eng.timer.start("train")

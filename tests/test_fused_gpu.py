@@ -265,3 +265,33 @@ def test_fused_evaluation_matches_the_per_client_loop(tmp_path):
         assert abs(rec["Loss"] - ref["Loss"]) < 2e-2 * max(1.0, abs(ref["Loss"]))
         assert abs(rec["top1"] - ref["top1"]) <= 10.0 + 1e-6           # at most 2 of 20 borderline samples flip
     m.train()
+
+
+@pytest.mark.parametrize("agg,attack", [("trimmedmean", "alie"), ("median", "ipm"), ("mean", "alie"), ("mean", None)])
+def test_pipelined_aggregation_equals_unpipelined(agg, attack, tmp_path, monkeypatch):
+    """Whole-round graph with the aggregation of finished layers overlapping the rest of the backward pass (side
+    stream, windows reported by the fused ResNet step) == the same graph with one aggregation after training."""
+    from blades_b200 import Simulator
+    from blades_b200.datasets import synthetic_fldataset
+    from blades_b200.models import resnet18
+    res, chunks = [], []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("BLADES_AGG_PIPELINE", flag)
+        ds = synthetic_fldataset(8, shape=(3, 32, 32), num_classes=10, train_bs=8, train_per_client=16, test_per_client=8,
+                                 seed=2)
+        akw = {"num_clients": 8, "num_byzantine": 2} if attack == "alie" else None
+        sim = Simulator(ds, num_byzantine=2 if attack else 0, attack=attack, attack_kws=akw, aggregator=agg,
+                        aggregator_kws={"nb": 2} if agg == "trimmedmean" else None, use_cuda=True, seed=1,
+                        log_path=str(tmp_path / f"p{flag}"), progress=False)
+        torch.manual_seed(3)
+        m = resnet18(num_classes=10)
+        sim.run(m, global_rounds=6, local_steps=1, server_lr=1.0, client_lr=0.05, validate_interval=6)
+        sts = [st for st in sim.engine._round_graphs.values() if "graph" in st]
+        assert sts, "round graph was not captured"
+        chunks.append(sts[0].get("chunks"))
+        res.append(sim.engine.gflat.theta.detach().cpu().clone())
+    assert chunks[0] is not None and len(chunks[0]) >= 3, chunks[0]          # layer4+fc | layer3 | rest
+    assert chunks[0][0][1] == res[0].numel() and chunks[0][-1][0] == 0
+    assert all(a[0] == b[1] for a, b in zip(chunks[0][:-1], chunks[0][1:]))  # contiguous, descending
+    assert chunks[1] is None
+    assert torch.equal(res[0], res[1]), (res[0] - res[1]).abs().max()
