@@ -11,6 +11,7 @@
 // The result is written to every replica and theta += lr*agg is applied in the same kernel.
 #pragma once
 #include "common.cuh"
+#include "tc_common.cuh"
 #include <cstdlib>
 
 // Compare-exchange formulations.  The networks are bound by the ALU pipe (FMNMX issues every 2nd cycle per SM
@@ -191,13 +192,78 @@ coord_select_part_kernel(const __grid_constant__ SelectParams p) {
     bl_epilogue_store(p.ep, c, bl_trimmed_partition<NP, MIX>(a, b, m, f));
 }
 
-static int select_block_size(int kmax) {
+// ---------------------------------------------------------------------------------------------
+// Partition-only trimmed mean fed by bulk copies (the TMA engine's 1-D form, cp.async.bulk): a persistent CTA walks
+// tiles of 128 coordinates; warp 0 issues one 512 B bulk copy per client row (local HBM or a peer's rows over NVLink)
+// into a [NP][128] shared-memory tile, completion is counted on an mbarrier, every thread then takes its coordinate's
+// NP values with immediate-offset LDS.  The per-row 64-bit address arithmetic (2 ALU-pipe IADD3 per row and THREAD in
+// the LDG form -- 15 % of the pipe that bounds this kernel) is done once per row and TILE by the issuing lanes, and
+// the next tile's copies fly while the current one is sorted (registers hold the values, so one buffer suffices).
+constexpr int kStageTile = 128;
+
+template <int NP> struct StageBlocks { static constexpr int kPerSM = NP <= 80 ? 5 : (NP <= 104 ? 4 : 3); };
+
+template <int NP, int MIX>
+__global__ void __launch_bounds__(kStageTile, StageBlocks<NP>::kPerSM)
+coord_select_part_stage_kernel(const __grid_constant__ SelectParams p) {
+    extern __shared__ __align__(128) unsigned char stage_smem[];
+    float* tile = reinterpret_cast<float*>(stage_smem);                              // [NP][kStageTile]
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage_smem + (size_t)NP * kStageTile * sizeof(float));
+    constexpr int H = NP / 2;
+    const int tid = threadIdx.x;
+    const long long n_tiles = (p.c1 - p.c0) / kStageTile;                            // whole tiles only (launcher)
+    if (tid == 0) { bl::mbar_init(full, 1); bl::fence_barrier_init(); }
+    __syncthreads();
+
+    auto issue = [&](long long t) {          // warp 0, all lanes: rows lane, lane + 32, ...
+        const long long c = p.c0 + t * kStageTile;
+        if (tid == 0) bl::mbar_arrive_expect_tx(full, (uint32_t)(NP * kStageTile * sizeof(float)));
+        __syncwarp();
+        for (int i = tid; i < NP; i += 32) {
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                :: "r"(bl::smem_u32(tile + i * kStageTile)), "l"(p.rows[i] + c), "r"((uint32_t)(kStageTile * sizeof(float))),
+                   "r"(bl::smem_u32(full)) : "memory");
+        }
+    };
+
+    long long t = blockIdx.x;
+    if (t < n_tiles && tid < 32) issue(t);
+    uint32_t parity = 0;
+    const int f = p.n_virtual;
+    for (; t < n_tiles; t += gridDim.x) {
+        float a[H], b[H];
+        bl::mbar_wait(full, parity);
+        parity ^= 1u;
+#pragma unroll
+        for (int i = 0; i < H; ++i) a[i] = tile[i * kStageTile + tid];
+#pragma unroll
+        for (int i = 0; i < H; ++i) b[i] = tile[(H + i) * kStageTile + tid];
+        __syncthreads();                                                             // everyone has its values
+        const long long tn = t + gridDim.x;
+        if (tn < n_tiles && tid < 32) issue(tn);                                     // refill while this tile is sorted
+        float total = bl_total<NP>(a, b);
+        if (bl_nonfinite(total)) {
+#pragma unroll
+            for (int i = 0; i < H; ++i) { a[i] = bl_sanitize(a[i]); b[i] = bl_sanitize(b[i]); }
+            total = bl_total<NP>(a, b);
+        }
+        float m = 0.f;
+        if (f > 0) m = p.n_stat == NP ? bl_virtual_value_all<NP>(a, b, total, p.virt_kind, p.virt_param)
+                                      : bl_virtual_value<NP>(a, b, p.n_stat, p.virt_kind, p.virt_param);
+        bl_epilogue_store(p.ep, p.c0 + t * kStageTile + tid, bl_trimmed_partition<NP, MIX>(a, b, m, f));
+    }
+}
+
+static int select_block_size(int kmax, bool partition) {
     static int forced = -1;
     if (forced < 0) {
         const char* e = getenv("BLADES_SELECT_BLOCK");
         forced = e ? atoi(e) : 0;
     }
-    int b = forced > 0 ? forced : 128;       // measured best of {128, 192, 256, 320, 384, 512} with the mixed compare-exchanges
+    // measured (profiles/kernel_bench_r2.txt): the partition kernel (two half sorts) is fastest with 128-thread
+    // blocks, the full networks (more straight-line code per warp) with 256
+    int b = forced > 0 ? forced : (partition ? 128 : 256);
     if (b > kmax) b = kmax;
     return (b / 32) * 32;
 }
@@ -221,6 +287,44 @@ static int select_ce_mix() {
     return v;
 }
 static bool select_imad_enabled() { return select_ce_mix() != 0; }
+
+static bool select_staged_enabled() {
+    // opt-in: measured SLOWER than the LDG form on B200 so far (1.23 vs 0.95 ms at the headline shape,
+    // profiles/kernel_bench_r2.txt) -- kept for the ncu comparison, BLADES_SELECT_STAGED=1 enables it
+    static const bool on = [] { const char* e = getenv("BLADES_SELECT_STAGED"); return e && e[0] == '1'; }();
+    return on;
+}
+
+// Bulk-copy staged form: whole 128-coordinate tiles whose row segments are 16 B aligned; the launcher hands the
+// remaining (< 128, or misaligned) coordinates to the LDG form.  Returns the number of coordinates it covered.
+template <int NP>
+static long long launch_partition_staged(const SelectParams& p, cudaStream_t st) {
+    if (!select_staged_enabled() || select_ce_mix() == 0 || (p.c0 % 4) != 0) return 0;
+    for (int i = 0; i < NP; ++i)
+        if ((uintptr_t)p.rows[i] % 16 != 0) return 0;
+    const long long n_tiles = (p.c1 - p.c0) / kStageTile;
+    if (n_tiles < 1) return 0;
+    const size_t smem = (size_t)NP * kStageTile * sizeof(float) + 16;
+    static int sms = 0;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(coord_select_part_stage_kernel<NP, kSelectMix>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem) != cudaSuccess) return 0;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        attr = true;
+    }
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm > StageBlocks<NP>::kPerSM) per_sm = StageBlocks<NP>::kPerSM;
+    if (per_sm < 1) return 0;
+    long long grid = (long long)sms * per_sm;
+    if (grid > n_tiles) grid = n_tiles;
+    SelectParams q = p;
+    q.c1 = p.c0 + n_tiles * kStageTile;
+    coord_select_part_stage_kernel<NP, kSelectMix><<<(unsigned)grid, kStageTile, smem, st>>>(q);
+    return n_tiles * kStageTile;
+}
 
 template <int NP>
 static bool launch_partition(const SelectParams& p, unsigned grid, int block, cudaStream_t st) {
@@ -247,9 +351,18 @@ static cudaError_t launch_small(const SelectParams& p, cudaStream_t st) {
     const long long cols = p.c1 - p.c0;
     if (cols <= 0) return cudaSuccess;
     if (p.c1 > 0xFFFFFFFFLL) return cudaErrorInvalidValue;      // 32-bit element offsets
-    const int block = select_block_size(SelectBlock<NP>::kMax);
+    if constexpr (NP % 8 == 0) {
+        if (partition_applies(p, NP)) {
+            SelectParams q = p;
+            q.c0 += launch_partition_staged<NP>(p, st);            // whole aligned tiles through the bulk-copy form
+            if (q.c0 >= q.c1) return cudaGetLastError();
+            const int pblock = select_block_size(SelectBlock<NP>::kMax, true);
+            launch_partition<NP>(q, (unsigned)((q.c1 - q.c0 + pblock - 1) / pblock), pblock, st);
+            return cudaGetLastError();
+        }
+    }
+    const int block = select_block_size(SelectBlock<NP>::kMax, false);
     const unsigned grid = (unsigned)((cols + block - 1) / block);
-    if (launch_partition<NP>(p, grid, block, st)) return cudaGetLastError();
     if (select_imad_enabled()) {
         if (p.mode == 0) coord_select_kernel<NP, 0, kSelectMix><<<grid, block, 0, st>>>(p);
         else coord_select_kernel<NP, 1, kSelectMix><<<grid, block, 0, st>>>(p);

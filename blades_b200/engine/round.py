@@ -986,6 +986,9 @@ class RoundEngine:
         """Dense [N, d] on every rank (escape hatch for custom callbacks/aggregators)."""
         if not self.world.distributed:
             return self.U
+        import os
+        if os.environ.get("BLADES_FORBID_DENSE_GATHER", "0") == "1":
+            raise RuntimeError("dense [N, d] gather requested while BLADES_FORBID_DENSE_GATHER=1")
         import torch.distributed as dist
         nmax = max(self.shard_sizes)
         pad = torch.zeros(nmax, self.d, device=self.U.device)

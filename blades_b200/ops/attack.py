@@ -13,14 +13,16 @@ __all__ = ["fill_normal_", "attack_rows"]
 _counter = [0]
 
 
-def fill_normal_(row: torch.Tensor, mean: float, std: float, seed: int = None) -> torch.Tensor:
-    """In-place N(mean, std) fill with the in-kernel Philox generator."""
+def fill_normal_(row: torch.Tensor, mean: float, std: float, seed: int = None, offset: int = None) -> torch.Tensor:
+    """In-place N(mean, std) fill with the in-kernel Philox generator.  ``offset``: position in the Philox stream
+    (in 128-bit blocks); default = a process-wide running counter."""
     assert row.is_cuda and row.dtype == torch.float32 and row.is_contiguous()
     lib = _loader.cuda_lib()
     if seed is None:
         seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
-    offset = _counter[0]
-    _counter[0] += (row.numel() + 3) // 4
+    if offset is None:
+        offset = _counter[0]
+        _counter[0] += (row.numel() + 3) // 4
     lib.bl_fill_normal.argtypes = [C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_ulonglong,
                                    C.c_ulonglong, C.c_void_p]
     _loader.check(lib.bl_fill_normal(row.data_ptr(), row.numel(), float(mean), float(std), seed, offset,

@@ -292,6 +292,17 @@ class Simulator(object):
         eng.timer.start("aggregate")
         callbacks = self._active_callbacks()
         virtual = self._cached_virtual()
+        self._round_index = int(global_round)
+        if virtual is None and callbacks and self.world.distributed and \
+                all(getattr(getattr(cb, "__self__", None), "row_local_attack", False) for cb in callbacks):
+            # every attacker only rewrites ITS OWN row (NoiseClient): the rank that owns the client runs the callback
+            # on the row where it lives -- no [N, d] gather over NCCL, no write-back (reference noiseclient.py:16-25)
+            mine = set(eng.local_idx)
+            index = {id(c): i for i, c in enumerate(self.get_clients())}
+            for cb in callbacks:
+                if index.get(id(cb.__self__)) in mine:
+                    cb(self)
+            callbacks = []
         if virtual is None and callbacks:
             if self.world.distributed:
                 dense = eng.gather_dense()

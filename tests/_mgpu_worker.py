@@ -27,7 +27,7 @@ def main():
                     use_cuda=True, seed=1, log_path=os.path.join(out_dir, f"logs_{world.size}"), progress=False)
     torch.manual_seed(5)
     m = MLP() if model_name == "mlp" else resnet18(10)
-    sim.run(m, global_rounds=3, local_steps=1, server_lr=1.0, client_lr=0.05, validate_interval=3)
+    sim.run(m, global_rounds=4, local_steps=1, server_lr=1.0, client_lr=0.05, validate_interval=4)
     torch.cuda.synchronize()
     vec = torch.cat([p.detach().reshape(-1) for p in m.parameters()]).cpu()
     torch.save(vec, os.path.join(out_dir, f"theta_{agg}_{attack}_{model_name}_{world.size}_{world.rank}.pt"))
