@@ -31,6 +31,10 @@ class Fltrust(_BaseAggregator):
 
     def aggregate(self, matrix, trusted: Optional[int] = None):
         t = self.trusted_index if trusted is None else trusted
+        dg = matrix.gram_device()
+        if dg is not None:               # trust scores on the device (csrc/cuda/gram_solve.cu): no host sync
+            from ..ops import gram_solve
+            return matrix.combine(gram_solve.fltrust_weights(dg, t))
         return matrix.combine(gops.fltrust_weights(matrix.gram(), t))
 
     def __str__(self):

@@ -252,3 +252,31 @@ extern "C" int bl_pad_rows(const float* src, float* dst, long long rows, int col
     pad_rows_kernel<<<pool_grid(rows * ldd), 256, 0, (cudaStream_t)stream>>>(src, dst, rows, cols, lds, ldd);
     return (int)cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------------------------
+// out[i] = nan_to_num(a[i] - b[i]): the client update "theta_after - theta_before" of the time-sliced (fedavg /
+// custom-client) path, sanitised where it is produced (reference client.py:195-198) -- one streaming launch.
+__global__ void __launch_bounds__(256)
+diff_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n4,
+                 long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i];
+        reinterpret_cast<float4*>(out)[i] = make_float4(bl_sanitize(x.x - y.x), bl_sanitize(x.y - y.y),
+                                                        bl_sanitize(x.z - y.z), bl_sanitize(x.w - y.w));
+    }
+    for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = bl_sanitize(a[i] - b[i]);
+}
+
+extern "C" int bl_diff_rows(const float* a, const float* b, float* out, long long n, void* stream) {
+    if (n <= 0) return 0;
+    const bool vec = ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    const long long n4 = vec ? n / 4 : 0;
+    long long work = vec ? n4 : n;
+    unsigned grid = (unsigned)((work + 255) / 256);
+    if (grid > 148u * 8) grid = 148u * 8;
+    if (grid < 1) grid = 1;
+    diff_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, out, n4, n);
+    return (int)cudaGetLastError();
+}

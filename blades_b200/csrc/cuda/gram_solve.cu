@@ -196,6 +196,39 @@ gram_iter_kernel(const __grid_constant__ IterParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------- FLTrust
+// w_i = relu(cos(u_t, u_i)) * ||u_t|| / ||u_i|| / sum_j relu(cos(u_t, u_j)),  w_t = 0   (reference fltrust.py:25-37,
+// host twin aggregators/_gramops.py::fltrust_weights; torch CosineSimilarity eps semantics)
+struct TrustParams {
+    const float* G; const int* idx; int ld;
+    int n, trusted;
+    double eps;
+    float* w;
+};
+
+__global__ void __launch_bounds__(kSolveThreads)
+gram_fltrust_kernel(const __grid_constant__ TrustParams p) {
+    __shared__ double red[32];
+    const GramView g{p.G, p.idx, p.ld};
+    const int j = threadIdx.x, n = p.n, t = p.trusted;
+    double ts = 0.0, nrm = 1.0;
+    const double nrm_t = sqrt(fmax((double)g.at(t, t), 0.0));
+    if (j < n) {
+        nrm = sqrt(fmax((double)g.at(j, j), 0.0));
+        const double c = (double)g.at(t, j) / fmax(nrm_t * nrm, p.eps);
+        ts = (j == t) ? 0.0 : fmax(c, 0.0);
+    }
+    const double sum = block_sum(ts, red);
+    if (j < n) p.w[j] = (j == t) ? 0.f : (float)(ts * nrm_t / nrm / sum);
+}
+
+extern "C" int bl_gram_fltrust(const TrustParams* p, void* stream) {
+    if (p->n < 1 || p->n > BL_MAX_ROWS || p->trusted < 0 || p->trusted >= p->n) return -1;
+    gram_fltrust_kernel<<<1, kSolveThreads, 0, (cudaStream_t)stream>>>(*p);
+    return (int)cudaGetLastError();
+}
+extern "C" int bl_sizeof_trust_params() { return (int)sizeof(TrustParams); }
+
 extern "C" int bl_gram_iter(const IterParams* p, void* stream) {
     if (p->n < 1 || p->n > BL_MAX_ROWS) return -1;
     IterParams q = *p;

@@ -14,9 +14,12 @@
 //     NVLink mapping); SWIZZLE_128B, K-major; out-of-range rows/columns are zero-filled by TMA.
 //   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread issues
 //     tcgen05.mma.kind::tf32), warps 2-9 = converter (ncu showed the 4-warp converter, not HBM or the tensor
-//     pipe, pacing the pipeline), warps 2-5 also run the epilogue.  The converter sanitises NaN/inf
-//     (nan_to_num) and, for 3xTF32, splits x = hi + lo (hi = tf32-truncated) into two smem tiles so
-//     that  hi*hi + hi*lo + lo*hi  recovers ~fp32 accuracy (distances suffer cancellation).
+//     pipe, pacing the pipeline), warps 2-5 also run the epilogue.  The converter scans for NaN/inf
+//     (nan_to_num in place, rare) and, for 3xTF32, writes lo2 = 2 (x - trunc_tf32(x)) into a second smem tile:
+//     the TMA tile itself is the hi operand (the tensor core truncates), and  hi*hi^T + hi*lo2^T  symmetrised by
+//     the consumers equals hi*hi + hi*lo + lo*hi (~fp32 accuracy; distances suffer cancellation) with 2 MMAs and
+//     2 instead of 3 shared-memory passes per element -- shared-memory bandwidth was the limit of the 3-MMA form.
+//     NOTE: G is therefore NOT symmetric as written; every reader applies 0.5 (G + G^T).
 //   * pipeline: full[s] (TMA -> converter), ready[s] (converter -> MMA), empty[s] (tcgen05.commit ->
 //     TMA), done (last commit -> epilogue).
 #include "common.cuh"
@@ -165,11 +168,9 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
                                 const uint64_t a_hi = d0 + (uint64_t)((hi + a_off + koff) >> 4);
                                 const uint64_t b_hi = d0 + (uint64_t)((hi + b_off + koff) >> 4);
                                 bl::umma_tf32_e(d_tmem, a_hi, b_hi, idesc, (it > 0 || sl > 0 || k > 0) ? 1u : 0u);
-                                if (p.split3) {
-                                    const uint64_t a_lo = d0 + (uint64_t)((lo + a_off + koff) >> 4);
+                                if (p.split3) {      // + hi * (2 lo)^T; its transpose comes from the symmetrisation
                                     const uint64_t b_lo = d0 + (uint64_t)((lo + b_off + koff) >> 4);
                                     bl::umma_tf32_e(d_tmem, a_hi, b_lo, idesc, 1u);
-                                    bl::umma_tf32_e(d_tmem, a_lo, b_hi, idesc, 1u);
                                 }
                             }
                         }
@@ -193,16 +194,25 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
 #pragma unroll 4
                 for (uint32_t g = ct; g < n16; g += kConvThreads) {
                     float4 x = *reinterpret_cast<float4*>(hi + g * 16u);
-                    x.x = bl_sanitize(x.x); x.y = bl_sanitize(x.y); x.z = bl_sanitize(x.z); x.w = bl_sanitize(x.w);
-                    float4 h;
-                    h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-                    h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-                    h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-                    h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-                    *reinterpret_cast<float4*>(hi + g * 16u) = h;
-                    if (p.split3)
-                        *reinterpret_cast<float4*>(lo + g * 16u) =
-                            make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+                    // The tile TMA wrote IS the hi operand: kind::tf32 reads the top 19 bits of each fp32 word, i.e. it
+                    // truncates exactly like `& 0xFFFFE000` -- no rewrite.  Only a non-finite value (rows are sanitised
+                    // where they are produced, so this is the rare path) is replaced in place by nan_to_num.
+                    const bool bad = !(fabsf(x.x) <= FLT_MAX) || !(fabsf(x.y) <= FLT_MAX) || !(fabsf(x.z) <= FLT_MAX) ||
+                                     !(fabsf(x.w) <= FLT_MAX);
+                    if (bad) {
+                        x.x = bl_sanitize(x.x); x.y = bl_sanitize(x.y); x.z = bl_sanitize(x.z); x.w = bl_sanitize(x.w);
+                        *reinterpret_cast<float4*>(hi + g * 16u) = x;
+                    }
+                    if (p.split3) {
+                        // lo tile = 2 * (x - trunc_tf32(x)): the MMA issuer adds hi*hi^T + hi*(2 lo)^T, and every consumer
+                        // of G symmetrises it (0.5 (G + G^T) = hi hi^T + hi lo^T + lo hi^T) -- 2 MMAs instead of 3
+                        float4 l;
+                        l.x = 2.f * (x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
+                        l.y = 2.f * (x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
+                        l.z = 2.f * (x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
+                        l.w = 2.f * (x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+                        *reinterpret_cast<float4*>(lo + g * 16u) = l;
+                    }
                 }
                 }
                 bl::fence_proxy_async_smem();                      // generic writes -> visible to UMMA
@@ -224,9 +234,13 @@ gram_tcgen05_kernel(const __grid_constant__ GramParams p) {
                     bl::tmem_ld_32x32(taddr, v);
                     if (row < p.rows_covered) {
                         float* dst = p.gram + (size_t)row * p.ld_gram + c;
+                        // rows_covered is a multiple of 8 and dst is 128 B aligned: whole 16 B groups, one vector
+                        // reduction per 4 accumulators (red.global.add.v4.f32, sm_90+)
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (c + j < p.rows_covered) atomicAdd(dst + j, v[j]);
+                        for (int j = 0; j < 32; j += 4)
+                            if (c + j < p.rows_covered)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                                             :: "l"(dst + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
                     }
                 }
             }

@@ -90,6 +90,18 @@ class PhaseTimer:
         return out
 
 
+def _diff(after: torch.Tensor, before: torch.Tensor, out: torch.Tensor) -> None:
+    """``out = nan_to_num(after - before)``: the time-sliced client update, sanitised where it is produced (reference
+    client.py:195-198); our streaming kernel on CUDA, torch on the CPU."""
+    if out.is_cuda and out.dtype == torch.float32 and after.is_contiguous() and before.is_contiguous() \
+            and out.is_contiguous():
+        from ..ops import fused as _kf
+        _kf.diff_rows(after, before, out)
+    else:
+        torch.sub(after, before, out=out)
+        torch.nan_to_num_(out)
+
+
 class _AggPipeline:
     """Pipelined aggregation inside the whole-round graph.  ``progress(lo)`` (called by the backward pass) says that
     every update coordinate ``>= lo`` is final; once enough of them have accumulated, the aggregation of that window
@@ -810,7 +822,7 @@ class RoundEngine:
                 with torch.no_grad():
                     w.theta.add_(w.grad, alpha=-lr * sign)
         with torch.no_grad():
-            torch.sub(w.theta, g.theta, out=scratch)
+            _diff(w.theta, g.theta, scratch)
         return loss.detach()
 
     def _slice_workers(self, k: int):
@@ -936,7 +948,7 @@ class RoundEngine:
             with torch.no_grad():
                 if not self.wflat.is_aliased():
                     self.wflat.realias()
-                torch.sub(self.wflat.theta, self.gflat.theta, out=self.U[r])
+                _diff(self.wflat.theta, self.gflat.theta, self.U[r])
                 c._state["saved_update"] = self.U[r]
         c.model = None
         c.optimizer = None

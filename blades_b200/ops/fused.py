@@ -29,6 +29,7 @@ def _lib():
         lib.bl_client_ce.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp]
         lib.bl_client_colsum.argtypes = [vp, vp, i, i, i, ll, ll, f, vp]
         lib.bl_pad_rows.argtypes = [vp, vp, ll, i, ll, i, vp]
+        lib.bl_diff_rows.argtypes = [vp, vp, vp, ll, vp]
         _typed = True
     return lib
 
@@ -130,3 +131,13 @@ def pad_rows(src: torch.Tensor, ld: Optional[int] = None) -> torch.Tensor:
                                      _loader.stream_ptr(src.device)), "pad_rows")
     _loader.count_launch()
     return dst
+
+
+def diff_rows(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """``out = nan_to_num(a - b)`` for flat fp32 CUDA vectors (the time-sliced client update), one own launch."""
+    assert a.is_cuda and a.dtype == b.dtype == out.dtype == torch.float32
+    assert a.is_contiguous() and b.is_contiguous() and out.is_contiguous() and a.numel() == b.numel() == out.numel()
+    _loader.check(_lib().bl_diff_rows(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(),
+                                      _loader.stream_ptr(a.device)), "diff_rows")
+    _loader.count_launch()
+    return out

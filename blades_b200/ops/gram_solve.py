@@ -12,7 +12,7 @@ import torch
 
 from . import _loader
 
-__all__ = ["DeviceGram", "enabled", "krum_weights", "weiszfeld_weights", "centered_clip_coeffs"]
+__all__ = ["DeviceGram", "enabled", "krum_weights", "weiszfeld_weights", "centered_clip_coeffs", "fltrust_weights"]
 
 
 def enabled() -> bool:
@@ -45,6 +45,11 @@ class IterParams(C.Structure):
                 ("maxiter", C.c_int), ("compounding", C.c_int), ("eps", C.c_double), ("ftol", C.c_double),
                 ("tau", C.c_double), ("alphas", C.c_void_p), ("gs", C.c_void_p), ("use_smem", C.c_int),
                 ("w", C.c_void_p), ("iters", C.c_void_p)]
+
+
+class TrustParams(C.Structure):
+    _fields_ = [("G", C.c_void_p), ("idx", C.c_void_p), ("ld", C.c_int), ("n", C.c_int), ("trusted", C.c_int),
+                ("eps", C.c_double), ("w", C.c_void_p)]
 
 
 _SCRATCH = {}
@@ -118,3 +123,17 @@ def weiszfeld_weights(dg: DeviceGram, alphas, maxiter: int, eps: float, ftol: fl
 def centered_clip_coeffs(dg: DeviceGram, tau: float, n_iter: int) -> torch.Tensor:
     """Coefficients over ``[u_0 .. u_{n-2}, m_prev]`` (the last Gram row is the previous momentum)."""
     return _iter(dg, 1, n_iter, False, 0.0, 0.0, tau, None)[0]
+
+
+def fltrust_weights(dg: DeviceGram, trusted: int, eps: float = 1e-6) -> torch.Tensor:
+    """Trust-score weights of every row against row ``trusted`` (its own weight is 0)."""
+    lib = _lib()
+    assert lib.bl_sizeof_trust_params() == C.sizeof(TrustParams)
+    dev = dg.G.device
+    w = torch.empty(dg.n, dtype=torch.float32, device=dev)
+    p = TrustParams()
+    p.G, p.idx, p.ld, p.n, p.trusted = dg.G.data_ptr(), dg.idx.data_ptr(), dg.G.stride(0), dg.n, int(trusted)
+    p.eps, p.w = float(eps), w.data_ptr()
+    _loader.check(lib.bl_gram_fltrust(C.byref(p), _loader.stream_ptr(dev)), "gram_fltrust")
+    _loader.count_launch()
+    return w

@@ -65,6 +65,19 @@ def test_device_centered_clip_matches_host(n, tau, iters):
     np.testing.assert_allclose(c, want, rtol=2e-5, atol=1e-8)
 
 
+@pytest.mark.parametrize("n,t", [(10, 0), (100, 37), (300, 299)])
+def test_device_fltrust_matches_host(n, t):
+    from blades_b200.aggregators import _gramops as gops
+    from blades_b200.ops import gram_solve
+    u = _matrix(n, 8192, 5 * n, outliers=n // 4)
+    dg = _dg(u)
+    G = dg.dense().double().cpu().numpy()
+    want = gops.fltrust_weights(G, t)
+    w = gram_solve.fltrust_weights(dg, t).cpu().numpy()
+    np.testing.assert_allclose(w, want, rtol=2e-5, atol=1e-9)
+    assert w[t] == 0.0
+
+
 def test_combine_reads_device_weights_and_skips_zero_rows():
     from blades_b200.parallel.matrix import LocalMatrix
     u = _matrix(50, 30001, 5)
@@ -83,7 +96,8 @@ def test_combine_reads_device_weights_and_skips_zero_rows():
 @pytest.mark.parametrize("name,kws", [("krum", dict(num_clients=30, num_byzantine=6)),
                                       ("multikrum", dict(num_byzantine=6)),
                                       ("geomed", dict(maxiter=50)), ("geomed", dict(maxiter=50, compat=False)),
-                                      ("centeredclipping", dict(tau=0.05, n_iter=3))])
+                                      ("centeredclipping", dict(tau=0.05, n_iter=3)),
+                                      ("fltrust", dict(trusted_index=4))])
 def test_aggregators_device_solve_equals_host_solve(name, kws, monkeypatch):
     import blades_b200.aggregators as A
     cls = {k.lower(): v for k, v in vars(A).items() if isinstance(v, type)}[name]
