@@ -164,10 +164,12 @@ def run_ours(args) -> dict:
     # ---------------- end-to-end through the public API ----------------
     h2d = d2h = 0
     e2e_ms, e2e_note, per_round = None, "", []
+    issued = []                                            # host time of every round's issue part (diagnostic)
 
     def e2e_phase():
         nonlocal d2h
         rounds = []
+        issued.clear()
         for r in range(max(args.warmup, 10)):       # untimed: also absorbs one-off host stalls after the phase switch
             one_round(r)
             float(eng.last_client_losses.mean()) if eng.last_client_losses is not None else None
@@ -177,6 +179,7 @@ def run_ours(args) -> dict:
         for r in range(args.steps):
             tr = time.perf_counter()
             one_round(r)                                   # host indices -> gather from pinned host memory -> round
+            issued.append((time.perf_counter() - tr) * 1e3)
             if eng.last_client_losses is not None:
                 loss_host = eng.last_client_losses.cpu()   # D2H read of the step's result
                 d2h = loss_host.numel() * loss_host.element_size()
@@ -223,6 +226,10 @@ def run_ours(args) -> dict:
                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                       "round_ms_median_rank0": sorted(per_round)[len(per_round) // 2], "round_ms_max_rank0": max(per_round),
                       "note": e2e_note,
+                      # the slowest round of every rank: (round index, total ms, of which host issue ms) -- where a stall sits
+                      "slowest_round_per_rank": world.all_gather_object(
+                          (per_round.index(max(per_round)), round(max(per_round), 2),
+                           round(issued[per_round.index(max(per_round))], 2)) if per_round and issued else None),
                       "h2d_mechanism": ("gather kernel reading the pinned host shards over PCIe (zero-copy) + index upload"
                                         if eng.prefetch and any(eng._zc_plans.values())
                                         else "pinned staging buffer + cudaMemcpyAsync")}

@@ -4,7 +4,10 @@ replica of every trainer shard.
 One symmetric allocation per rank (``torch.distributed._symmetric_memory``: CUDA VMM + IPC handle
 exchange; NVLS multicast object when the fabric supports it), laid out identically everywhere:
 
-    [ U_g : nmax rows x ld floats ][ agg : ld ][ theta : ld ][ scratch : 512 x 512 ]
+    [ U_g : nmax rows x ld floats ][ agg : ld ][ theta : ld ][ scratch : 512 x 512 ][ recv : n_total x recv_ld ]
+
+``recv`` is the landing zone of the push-mode aggregation: row i holds client i's values of the coordinates THIS rank
+aggregates (its shard of every window), written by the owner of row i with copy-engine DMAs over NVLink.
 
 (``scratch`` holds the N x N Gram partials that are summed inside the NVSwitch, ``reduce_scratch``)
 
@@ -52,7 +55,9 @@ class SymmetricUpdates:
         self.n_local = self.shard_sizes[world.rank]
         self.n_total = sum(self.shard_sizes)
         self.scratch_floats = SCRATCH_FLOATS
-        total = self.nmax * self.ld + 2 * self.ld + self.scratch_floats
+        # push-mode landing zone: every rank's shard of every aggregation window (<= 16 windows, 128-float alignment)
+        self.recv_ld = round_up((d + world.size - 1) // world.size + 128 * 17, 64) if world.size > 1 else 0
+        total = self.nmax * self.ld + 2 * self.ld + self.scratch_floats + self.n_total * self.recv_ld
         self.buf = symm_mem.empty((total,), dtype=torch.float32, device=world.device)
         self.buf.zero_()
         self.handle = symm_mem.rendezvous(self.buf, dist.group.WORLD)
@@ -65,6 +70,8 @@ class SymmetricUpdates:
         self.theta = self.buf[self.off_theta: self.off_theta + d]
         self.off_scratch = self.off_theta + self.ld
         self.scratch = self.buf[self.off_scratch: self.off_scratch + self.scratch_floats]
+        self.off_recv = self.off_scratch + self.scratch_floats
+        self.row0 = [sum(self.shard_sizes[:r]) for r in range(world.size)]       # first global row of every rank
         self.multicast_ptr = int(self.handle.multicast_ptr) if getattr(self.handle, "multicast_ptr", 0) else 0
         if os.environ.get("BLADES_MULTIMEM", "1") == "0":       # A/B switch: per-peer stores / P2P reduction
             self.multicast_ptr = 0
@@ -107,6 +114,14 @@ class SymmetricUpdates:
                        self.multicast_ptr + self.off_scratch * 4 if self.multicast_ptr else 0,
                        count, self.world.rank, self.world.size, self.world.device)
         self.barrier()
+
+    def window_span(self, lo: int, hi: int) -> int:
+        """Columns a window occupies in every rank's ``recv`` rows (identical on all ranks): the longest shard."""
+        return max(c1 - c0 for c0, c1 in coordinate_shards(hi - lo, self.world.size))
+
+    def recv_row_ptr(self, rank: int, global_row: int, col: int = 0) -> int:
+        """Address (in this process: local or peer mapping) of ``recv[global_row][col]`` on ``rank``."""
+        return self.base_ptrs[rank] + (self.off_recv + global_row * self.recv_ld + col) * 4
 
     def block_descs(self):
         """(base_ptr, ld, rows) of every rank's row block, in global row order."""

