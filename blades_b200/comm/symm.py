@@ -115,6 +115,13 @@ class SymmetricUpdates:
                        count, self.world.rank, self.world.size, self.world.device)
         self.barrier()
 
+    def push_streams(self):
+        """Side streams for the push-mode DMAs (one per destination rank, ``BLADES_PUSH_STREAMS`` caps the number)."""
+        if getattr(self, "_push_streams", None) is None:
+            k = max(1, min(self.world.size, int(os.environ.get("BLADES_PUSH_STREAMS", "8"))))
+            self._push_streams = [torch.cuda.Stream(device=self.world.device) for _ in range(k)]
+        return self._push_streams
+
     def window_span(self, lo: int, hi: int) -> int:
         """Columns a window occupies in every rank's ``recv`` rows (identical on all ranks): the longest shard."""
         return max(c1 - c0 for c0, c1 in coordinate_shards(hi - lo, self.world.size))

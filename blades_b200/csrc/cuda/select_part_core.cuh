@@ -9,7 +9,8 @@
 // A virtual value m of multiplicity f >= Q (ALIE / IPM rows) merges analytically: the lowest Q of the
 // merged multiset are the bottom-set members below m plus copies of m, so every bottom-set member x >= m stays
 // (contributing x) while a copy of m is trimmed instead -- and symmetrically at the top:
-//   kept = sum(middle) + sum_{x in Bot} max(x - m, 0) + sum_{x in Top} min(x - m, 0) + f*m,   N - 2Q values kept.
+//   kept = sum(middle) + sum_{x in Bot} max(x - m, 0) + sum_{x in Top} min(x - m, 0) + f*m,   N - 2Q values kept
+//        (= sum(middle) + sum_{x in Bot} max(x, m) + sum_{x in Top} min(x, m) + (f - 2Q)*m).
 // No large-minus-large cancellation: the middle is summed directly and the corrections are differences to m.
 #pragma once
 
@@ -76,12 +77,27 @@ BL_CORE_FN float bl_virtual_value_all(const float (&a)[NP / 2], const float (&b)
 
 // Trimmed mean of the NP real values (+ f copies of m), trimming Q = NP/4 from each end.  Requires f == 0 or f >= Q.
 // Destroys a and b (sorted in place).
-template <int NP, int MIX = 0>
+template <int NP, int MIX = 0, bool ROLL = false>
 BL_CORE_FN float bl_trimmed_partition(float (&a)[NP / 2], float (&b)[NP / 2], float m, int f) {
     static_assert(NP % 8 == 0 && NP >= 8 && NP <= 128, "halves must be SortNet sizes (multiples of 4)");
     constexpr int H = NP / 2, Q = NP / 4;
+    if (ROLL) {
+    // ONE copy of the half-size network in the instruction stream, executed twice: ncu's top stall of the unrolled
+    // form was "no_instruction" (the two inlined 305-comparator networks are ~27 KB of SASS, the whole kernel ~45 KB
+    // against a 32 KB L1.5 instruction cache, and 128-thread blocks run out of phase).  The halves trade places
+    // between the passes (register moves); the splits below are symmetric in (a, b), so no second exchange.
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+        SortNet<H>::template run<MIX>(a);
+        if (h == 0) {
+#pragma unroll
+            for (int i = 0; i < H; ++i) { const float t = a[i]; a[i] = b[i]; b[i] = t; }
+        }
+    }
+    } else {
     SortNet<H>::template run<MIX>(a);
     SortNet<H>::template run<MIX>(b);
+    }
     float mid0 = 0.f, mid1 = 0.f, ext0 = 0.f, ext1 = 0.f;
     if (f > 0) {                                               // uniform branch (kernel parameter)
 #pragma unroll
@@ -102,6 +118,8 @@ BL_CORE_FN float bl_trimmed_partition(float (&a)[NP / 2], float (&b)[NP / 2], fl
 #pragma unroll
         for (int i = 0; i < Q; ++i) mid1 += fminf(a[Q + i], b[H - 1 - i]);
     }
+    // (hoisting the "- m" out of the sums -- sum clip + (f - 2Q) m -- saves 2Q FADDs but lengthens live ranges enough
+    // to spill at several sizes; kept in the per-element form)
     const float kept = (mid0 + mid1) + (ext0 + ext1) + (float)f * (f > 0 ? m : 0.f);
     return kept / (float)(NP + f - 2 * Q);
 }

@@ -90,6 +90,18 @@ class PhaseTimer:
         return out
 
 
+class _HostRead:
+    """Pending pinned-memory copy: ``get()`` blocks until its event has completed and returns the host tensor."""
+    __slots__ = ("buf", "event")
+
+    def __init__(self, buf: torch.Tensor, event):
+        self.buf, self.event = buf, event
+
+    def get(self) -> torch.Tensor:
+        self.event.synchronize()
+        return self.buf
+
+
 def _diff(after: torch.Tensor, before: torch.Tensor, out: torch.Tensor) -> None:
     """``out = nan_to_num(after - before)``: the time-sliced client update, sanitised where it is produced (reference
     client.py:195-198); our streaming kernel on CUDA, torch on the CPU."""
@@ -737,6 +749,26 @@ class RoundEngine:
             t = self._clamps[key] = torch.tensor(
                 [float(self.clients[self.local_idx[r]].loss_clamp) for r in rows], device=self.device)
         return t
+
+    def losses_to_host_async(self) -> Optional["_HostRead"]:
+        """Start a device->host copy of this round's per-client losses into a pinned double buffer, stream ordered
+        after the round, and return a handle whose ``get()`` waits for THAT copy only.  Lets a driver loop issue round
+        r+1 (host indices, graph launch) before it reads the result of round r, so the host work of a round hides
+        behind the previous round's GPU time instead of leaving the GPU idle between rounds (the reference reads every
+        client's loss synchronously inside the training loop, client.py:190)."""
+        t = self.last_client_losses
+        if t is None or not t.is_cuda:
+            return None
+        slots = getattr(self, "_loss_slots", None)
+        if slots is None or slots[0][0].numel() != t.numel():
+            slots = self._loss_slots = [(torch.empty(t.numel(), dtype=t.dtype).pin_memory(), torch.cuda.Event())
+                                        for _ in range(2)]
+            self._loss_turn = 0
+        buf, ev = slots[self._loss_turn]
+        self._loss_turn ^= 1
+        buf.copy_(t.reshape(-1), non_blocking=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        return _HostRead(buf, ev)
 
     def _pipeline_enabled(self) -> bool:
         import os

@@ -24,11 +24,17 @@ from .matrix import UpdateMatrix, VirtualRows
 __all__ = ["ShardedMatrix"]
 
 
-def _push_enabled() -> bool:
-    """``BLADES_AGG_PUSH=0``: pull mode (kernels read peer rows with loads over NVLink) instead of the copy-engine
-    pushes + local reads."""
+def _push_enabled(world_size: int = 2) -> bool:
+    """Push mode (copy-engine DMAs of finished windows + local reads) or pull mode (kernels read peer rows with loads
+    over NVLink).  ``BLADES_AGG_PUSH`` = 1 / 0 forces one; the default follows the measurements on B200 NVSwitch nodes
+    (profiles/README.md): push wins while the per-GPU NVLink volume is large next to the backward pass it hides behind
+    (2 GPUs: 237 vs 199 rounds/s), pull wins at 8 GPUs (376 vs 344), where each DMA is small and the all-to-all of
+    eight ranks x seven destinations tops out at the same ~470 GB/s per GPU either way."""
     import os
-    return os.environ.get("BLADES_AGG_PUSH", "1") != "0"
+    v = os.environ.get("BLADES_AGG_PUSH", "auto")
+    if v in ("0", "1"):
+        return v == "1"
+    return world_size <= 4
 
 
 class ShardedMatrix(UpdateMatrix):
@@ -42,7 +48,7 @@ class ShardedMatrix(UpdateMatrix):
         self.step_applied = False
         self._synced = False
         self.recv_col = 0                # column of this window inside the recv rows (pipelined aggregation)
-        self.push = _push_enabled() and symm.world.size > 1 and symm.recv_ld > 0
+        self.push = _push_enabled(symm.world.size) and symm.world.size > 1 and symm.recv_ld > 0
 
     # ------------------------------------------------------------------ helpers
     def _cols(self):
@@ -83,12 +89,24 @@ class ShardedMatrix(UpdateMatrix):
                 runs.append((start, i))
                 start = None
         u0 = s.local_full.data_ptr()
+        # one stream per destination: the copies to different peers are independent DMAs (separate copy engines /
+        # NVLink ports); forked from and joined back into the calling stream, so they stay ordered after the training
+        # kernels and before the barrier (inside a graph capture these become parallel memcpy nodes)
+        cur = torch.cuda.current_stream(self.device)
+        pool = s.push_streams()
+        used = []
         for g, (d0, d1) in enumerate(self._shards()):
-            if g == me or d1 <= d0:
+            if g == me or d1 <= d0 or not runs:
                 continue
-            for (a, b) in runs:
-                nvls.copy2d(s.recv_row_ptr(g, row0 + a, self.recv_col), s.recv_ld * 4,
-                            u0 + (a * s.ld + d0) * 4, s.ld * 4, (d1 - d0) * 4, b - a, self.device)
+            st = pool[g % len(pool)]
+            st.wait_stream(cur)
+            used.append(st)
+            with torch.cuda.stream(st):
+                for (a, b) in runs:
+                    nvls.copy2d(s.recv_row_ptr(g, row0 + a, self.recv_col), s.recv_ld * 4,
+                                u0 + (a * s.ld + d0) * 4, s.ld * 4, (d1 - d0) * 4, b - a, self.device)
+        for st in used:
+            cur.wait_stream(st)
 
     def _ptrs(self, rows):
         """Row pointers for a kernel that reads coordinates ``self._cols()``: NVLink peer pointers (pull mode), or --

@@ -89,5 +89,8 @@ def test_hot_kernels_do_not_spill():
             if "part_stage" in name:          # opt-in bulk-copy staged form (measured slower): one 8-byte frame slot
                 assert int(stack) <= 16 and int(local) == 0, (name, stack, local)
                 continue
+            if "coord_select_part_kernel" in name:   # rolled half sorts: ptxas keeps up to 6 values in a 24 B frame
+                assert int(stack) <= 32 and int(local) == 0, (name, stack, local)
+                continue
             assert int(stack) == 0 and int(local) == 0, (name, stack, local)
             assert int(reg) <= 168, (name, reg)
