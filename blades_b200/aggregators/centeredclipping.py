@@ -45,7 +45,11 @@ class Centeredclipping(_BaseAggregator):
                 from ..ops import gram_solve
                 c = gram_solve.centered_clip_coeffs(dg, self.tau, self.n_iter)
                 new_m = matrix.combine(c, extra=m)
-                self.momentum = new_m.detach().clone()
+                if self.momentum is not None and self.momentum.is_cuda and self.momentum.shape == new_m.shape \
+                        and self.momentum.dtype == new_m.dtype and self.momentum.device == new_m.device:
+                    self.momentum.copy_(new_m)       # in place: a captured round keeps reading this very buffer
+                else:
+                    self.momentum = new_m.detach().clone()
                 return new_m
         if self.momentum is None:
             # m = 0: Gram row/col of zeros, no need to touch the device for it

@@ -59,7 +59,8 @@ class SymmetricUpdates:
         self.recv_ld = round_up((d + world.size - 1) // world.size + 128 * 17, 64) if world.size > 1 else 0
         total = self.nmax * self.ld + 2 * self.ld + self.scratch_floats + self.n_total * self.recv_ld
         self.buf = symm_mem.empty((total,), dtype=torch.float32, device=world.device)
-        self.buf.zero_()
+        from ..ops import nvls
+        nvls.zero_(self.buf)
         self.handle = symm_mem.rendezvous(self.buf, dist.group.WORLD)
         self.base_ptrs: List[int] = [int(p) for p in self.handle.buffer_ptrs]
         self.off_agg = self.nmax * self.ld

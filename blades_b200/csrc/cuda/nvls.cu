@@ -64,3 +64,9 @@ extern "C" int bl_copy2d_async(void* dst, long long dpitch, const void* src, lon
     return (int)cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width_bytes, (size_t)height,
                                   cudaMemcpyDefault, (cudaStream_t)stream);
 }
+
+// Zero fill by the driver's memset path (copy engine / memset node) -- no elementwise kernel launch.
+extern "C" int bl_memset_zero_async(void* dst, long long bytes, void* stream) {
+    if (bytes <= 0) return 0;
+    return (int)cudaMemsetAsync(dst, 0, (size_t)bytes, (cudaStream_t)stream);
+}

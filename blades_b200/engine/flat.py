@@ -90,11 +90,21 @@ class FlatParams:
                     p.data = p.data.to(self.device)
             for buf_name, buf in model.named_buffers():
                 buf.data = buf.data.to(self.device)
-            for s in self.specs:
-                p = self._by_name[s.name]
-                view = s.view(self.theta)
-                view.copy_(p.data.to(self.device, dtype))
-                p.data = view
+            if self.device.type == "cuda":
+                # lay the vector out on the HOST (the channels_last permutation of the conv weights is a strided CPU
+                # copy) and upload it with ONE memcpy: no per-parameter strided-copy kernels on the device
+                host = torch.empty(self.numel, dtype=dtype)
+                for s in self.specs:
+                    s.view(host).copy_(self._by_name[s.name].data.detach().to("cpu", dtype))
+                self.theta.copy_(host)
+                for s in self.specs:
+                    self._by_name[s.name].data = s.view(self.theta)
+            else:
+                for s in self.specs:
+                    p = self._by_name[s.name]
+                    view = s.view(self.theta)
+                    view.copy_(p.data.to(self.device, dtype))
+                    p.data = view
 
     # -- views -----------------------------------------------------------------
     def view_of(self, vec: torch.Tensor, spec: ParamSpec) -> torch.Tensor:

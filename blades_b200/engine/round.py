@@ -268,7 +268,11 @@ class RoundEngine:
         else:
             self.symm = None
             ld = (d + 63) // 64 * 64          # 256 B aligned rows: 16 B vector loads + TMA strides
-            self.U = torch.zeros(max(n_local, 1), ld, device=self.device, dtype=torch.float32)[:n_local, :d]
+            if self.device.type == "cuda":
+                from ..ops import nvls
+                self.U = nvls.zero_(torch.empty(max(n_local, 1), ld, device=self.device, dtype=torch.float32))[:n_local, :d]
+            else:
+                self.U = torch.zeros(max(n_local, 1), ld, device=self.device, dtype=torch.float32)[:n_local, :d]
 
     def _peer_access_everywhere(self) -> bool:
         """``BLADES_SYMM=0`` (set identically on every rank) disables the NVLink symmetric-memory path: rows are then
@@ -694,7 +698,7 @@ class RoundEngine:
             graph = torch.cuda.CUDAGraph()
             before = _loader.LAUNCHES
             try:
-                pipe = _AggPipeline(self, aggregate_fn) if self._pipeline_enabled() else None
+                pipe = _AggPipeline(self, aggregate_fn) if (self._pipeline_enabled() and getattr(self, "agg_windows_ok", True)) else None
                 with torch.cuda.graph(graph, stream=self._capture_stream(), capture_error_mode=_CAPTURE_MODE):
                     if pipe is None:
                         losses = self._batched_step(rows, lr, sx, sy)

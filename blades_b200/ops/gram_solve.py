@@ -53,6 +53,19 @@ class TrustParams(C.Structure):
 
 
 _SCRATCH = {}
+_IDX = {}
+
+
+def index_tensor(idx, device) -> torch.Tensor:
+    """Device int32 tensor of a logical -> padded row list, cached per (device, list): the list is the same every
+    round, and an H2D copy from pageable memory is not allowed while a CUDA graph is being captured."""
+    key = (torch.device(device).index or 0, tuple(idx))
+    t = _IDX.get(key)
+    if t is None:
+        if len(_IDX) > 64:
+            _IDX.clear()
+        t = _IDX[key] = torch.tensor(list(idx), dtype=torch.int32, device=device)
+    return t
 
 
 def _scratch(device) -> dict:

@@ -8,7 +8,7 @@ from typing import Sequence
 
 from . import _loader, _structs
 
-__all__ = ["allreduce", "copy2d"]
+__all__ = ["allreduce", "copy2d", "zero_"]
 
 
 class NvlsReduceParams(C.Structure):
@@ -37,3 +37,13 @@ def copy2d(dst_ptr: int, dst_pitch: int, src_ptr: int, src_pitch: int, width_byt
                                     C.c_void_p]
     _loader.check(lib.bl_copy2d_async(dst_ptr, dst_pitch, src_ptr, src_pitch, width_bytes, height,
                                       _loader.stream_ptr(device)), "copy2d_async")
+
+
+def zero_(t: "torch.Tensor") -> "torch.Tensor":
+    """Zero a contiguous CUDA tensor with ``cudaMemsetAsync`` (stream ordered; no fill kernel)."""
+    assert t.is_cuda and t.is_contiguous()
+    lib = _loader.cuda_lib()
+    lib.bl_memset_zero_async.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p]
+    _loader.check(lib.bl_memset_zero_async(t.data_ptr(), t.numel() * t.element_size(), _loader.stream_ptr(t.device)),
+                  "memset_zero")
+    return t

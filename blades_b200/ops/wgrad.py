@@ -35,7 +35,7 @@ def grouped_wgrad(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, alpha: fl
 _USE_IMPLICIT = os.environ.get("BLADES_IMPLICIT_WGRAD", "1") != "0"
 
 
-_IMPLICIT_MAX_T = int(os.environ.get("BLADES_IMPLICIT_MAX_T", "1024"))
+_IMPLICIT_MAX_T = int(os.environ.get("BLADES_IMPLICIT_MAX_T", "4096"))
 
 
 def conv_wgrad_implicit(gy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, n_clients: int, kernel, stride,
@@ -46,10 +46,11 @@ def conv_wgrad_implicit(gy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, n_
     gy: channels_last ``[NB, Cout, Ho, Wo]``; x: channels_last ``[NB, Cin, H, W]``;
     out: ``[n, Cout, kh*kw*Cin]`` window of the update matrix (physical channels_last weight order).
     Returns False when the shape is not supported (caller falls back to im2col + grouped GEMM), or -- unless
-    ``force`` -- when the per-client reduction length T = B*Ho*Wo exceeds ``BLADES_IMPLICIT_MAX_T`` (default 1024):
-    measured on B200 (profiles/round_kernels_r1.txt) the 4-D gather runs the long-K / small-output layers
-    (ResNet layer1: T = 2048, 64 x 576 outputs) at 329 us vs 162 us + ~100 us im2col for the explicit pair, while
-    it wins or ties from T = 512 down (and saves the im2col matrix)."""
+    ``force`` -- when the per-client reduction length T = B*Ho*Wo exceeds ``BLADES_IMPLICIT_MAX_T`` (default 4096).
+    History of that threshold: in round 1 the 4-D gather ran the long-K / small-output layers (ResNet layer1: T = 2048,
+    64 x 576 outputs) at 329 us vs 162 us + ~100 us im2col for the explicit pair and the limit was 1024; with the
+    warp-uniform issue loops and running stage counters of round 2 the implicit form wins there too -- headline round
+    6.67 -> 6.03 ms (150 -> 166 rounds/s, profiles/README.md) -- and saves the four im2col launches and matrices."""
     if not (_USE_KERNEL and _USE_IMPLICIT and gy.is_cuda):
         return False
     import ctypes as C

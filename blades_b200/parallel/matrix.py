@@ -275,7 +275,7 @@ def _local_gram_device(self, extra: Optional[torch.Tensor] = None):
     if r is None:
         return None
     out, idx = r
-    return gram_solve.DeviceGram(out, torch.tensor(idx, dtype=torch.int32, device=data.device), len(idx))
+    return gram_solve.DeviceGram(out, gram_solve.index_tensor(idx, data.device), len(idx))
 
 
 LocalMatrix.gram_device = _local_gram_device

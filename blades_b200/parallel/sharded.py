@@ -37,6 +37,31 @@ def _push_enabled(world_size: int = 2) -> bool:
     return world_size <= 4
 
 
+def push_plan(me: int, row0, n_local: int, ld: int, recv_ld: int, shards, recv_col: int, skip):
+    """The 2-D copies rank ``me`` issues to ship its rows' slices of the other ranks' coordinate ranges (pure host
+    logic, unit-tested without a GPU).  ``shards[g] = (d0, d1)``: coordinates rank g aggregates; ``skip``: global rows
+    nobody reads (replaced by virtual attack rows).  Returns ``(dst_rank, first_global_row, dst_col, src_offset_floats,
+    width_floats, n_rows)`` per copy: rows ``[first, first + n_rows)`` of the destination's landing zone, columns
+    ``[dst_col, dst_col + width)``, read from ``U_local`` at float offset ``src_offset`` with row pitch ``ld``."""
+    first = row0[me]
+    runs, start = [], None                          # maximal runs of consecutive local rows that are needed
+    for i in range(n_local + 1):
+        need = i < n_local and (first + i) not in skip
+        if need and start is None:
+            start = i
+        if not need and start is not None:
+            runs.append((start, i))
+            start = None
+    plan = []
+    for g, (d0, d1) in enumerate(shards):
+        if g == me or d1 <= d0:
+            continue
+        assert recv_col + (d1 - d0) <= recv_ld, "landing zone too small for this window"
+        for (a, b) in runs:
+            plan.append((g, first + a, recv_col, a * ld + d0, d1 - d0, b - a))
+    return plan
+
+
 class ShardedMatrix(UpdateMatrix):
     def __init__(self, symm, virtual: Optional[VirtualRows] = None):
         self.symm = symm
@@ -77,17 +102,8 @@ class ShardedMatrix(UpdateMatrix):
         that follows on every rank is what tells the aggregator that all pushes have landed."""
         from ..ops import nvls
         s = self.symm
-        me = s.world.rank
         skip = set(self.virtual.replaced) if (self.virtual is not None and self.virtual.count) else set()
-        row0 = s.row0[me]
-        runs, start = [], None                      # maximal runs of consecutive local rows that are needed
-        for i in range(s.n_local + 1):
-            need = i < s.n_local and (row0 + i) not in skip
-            if need and start is None:
-                start = i
-            if not need and start is not None:
-                runs.append((start, i))
-                start = None
+        plan = push_plan(s.world.rank, s.row0, s.n_local, s.ld, s.recv_ld, self._shards(), self.recv_col, skip)
         u0 = s.local_full.data_ptr()
         # one stream per destination: the copies to different peers are independent DMAs (separate copy engines /
         # NVLink ports); forked from and joined back into the calling stream, so they stay ordered after the training
@@ -95,16 +111,15 @@ class ShardedMatrix(UpdateMatrix):
         cur = torch.cuda.current_stream(self.device)
         pool = s.push_streams()
         used = []
-        for g, (d0, d1) in enumerate(self._shards()):
-            if g == me or d1 <= d0 or not runs:
-                continue
+        for g in sorted({c[0] for c in plan}):
             st = pool[g % len(pool)]
             st.wait_stream(cur)
             used.append(st)
             with torch.cuda.stream(st):
-                for (a, b) in runs:
-                    nvls.copy2d(s.recv_row_ptr(g, row0 + a, self.recv_col), s.recv_ld * 4,
-                                u0 + (a * s.ld + d0) * 4, s.ld * 4, (d1 - d0) * 4, b - a, self.device)
+                for (dst, grow, gcol, src_off, width, height) in plan:
+                    if dst == g:
+                        nvls.copy2d(s.recv_row_ptr(g, grow, gcol), s.recv_ld * 4, u0 + src_off * 4, s.ld * 4,
+                                    width * 4, height, self.device)
         for st in used:
             cur.wait_stream(st)
 
@@ -219,7 +234,7 @@ class ShardedMatrix(UpdateMatrix):
         if not gram_solve.enabled():
             return None
         out, idx = self._gram_scratch(extra)
-        return gram_solve.DeviceGram(out, torch.tensor(idx, dtype=torch.int32, device=self.device), len(idx))
+        return gram_solve.DeviceGram(out, gram_solve.index_tensor(idx, self.device), len(idx))
 
     def _gram_scratch(self, extra: Optional[torch.Tensor] = None):
         """Summed Gram accumulators in every rank's symmetric scratch region + the logical -> padded row list."""

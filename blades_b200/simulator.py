@@ -356,11 +356,18 @@ class Simulator(object):
     def _static_round_possible(self, local_steps: int) -> bool:
         """The round is a fixed sequence of device work (no host decisions): fedsgd on the batched engine,
         attack fused as virtual rows (or none), coordinate-wise built-in aggregator, fused SGD server step."""
-        from .aggregators import Mean, Median, Trimmedmean
+        from .aggregators import Centeredclipping, Fltrust, Geomed, Krum, Mean, Median, Multikrum, Trimmedmean
         eng = self.engine
         if local_steps != 1 or eng.device.type != "cuda" or eng.timer.enabled or not self._opts["fuse_server_step"]:
             return False
-        if type(self.aggregator) not in (Mean, Median, Trimmedmean) or not self.server._flat_fast_path_ok():
+        coordwise = type(self.aggregator) in (Mean, Median, Trimmedmean)
+        # Gram-based aggregators whose solver runs on the device (ops/gram_solve) are a fixed sequence of launches too:
+        # Gram pass -> (in-switch reduce) -> solver -> combine with device-resident weights
+        from .ops import gram_solve
+        devsolve = type(self.aggregator) in (Krum, Multikrum, Geomed, Centeredclipping, Fltrust) and gram_solve.enabled() \
+            and eng.use_kernels
+        eng.agg_windows_ok = coordwise          # only coordinate-wise aggregators can be pipelined window by window
+        if not (coordwise or devsolve) or not self.server._flat_fast_path_ok():
             return False
         if self._active_callbacks() and self._cached_virtual() is None:
             return False

@@ -360,9 +360,12 @@ def test_wgrad_padded_rows():
     assert (out.double() - ref).abs().max() <= 2e-3 * ref.abs().max() + 1e-4
 
 
-@pytest.mark.parametrize("agg,attack", [("trimmedmean", "alie"), ("median", "ipm"), ("mean", None), ("trimmedmean", "labelflipping")])
+@pytest.mark.parametrize("agg,attack", [("trimmedmean", "alie"), ("median", "ipm"), ("mean", None), ("trimmedmean", "labelflipping"),
+                                        ("krum", "labelflipping"), ("multikrum", "alie"), ("geomed", None),
+                                        ("centeredclipping", "signflipping")])
 def test_whole_round_graph_equals_eager(agg, attack, tmp_path, monkeypatch):
-    """Rounds 3+ replay one captured CUDA graph (train + fused attack/aggregate/server step): same result as eager."""
+    """Rounds 3+ replay one captured CUDA graph (train + fused attack/aggregate/server step): same result as eager.
+    The Gram-based aggregators join the graph because their solvers run on the device (ops/gram_solve)."""
     from blades_b200 import Simulator
     from blades_b200.datasets import synthetic_fldataset
     from blades_b200.models import MLP
@@ -373,7 +376,9 @@ def test_whole_round_graph_equals_eager(agg, attack, tmp_path, monkeypatch):
         ds = synthetic_fldataset(10, shape=(28, 28), train_bs=8, seed=3, separation=2.0)
         akw = {"num_clients": 10, "num_byzantine": 3} if attack == "alie" else None
         sim = Simulator(ds, num_byzantine=3 if attack else 0, attack=attack, attack_kws=akw, aggregator=agg,
-                        aggregator_kws={"nb": 3} if agg == "trimmedmean" else None, use_cuda=True, seed=1,
+                        aggregator_kws={"nb": 3} if agg == "trimmedmean" else (
+                            {"num_clients": 10, "num_byzantine": 3} if agg == "krum" else (
+                                {"num_byzantine": 3} if agg == "multikrum" else None)), use_cuda=True, seed=1,
                         log_path=str(tmp_path / f"l{flag}"), progress=False)
         torch.manual_seed(5)
         m = MLP()
