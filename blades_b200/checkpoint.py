@@ -15,6 +15,11 @@ One ``torch.save`` dict:
     config           {n_clients, d, world_size, format_version}
 
 Every rank holds identical server state, so rank 0 writes; every rank reads.
+
+Format 3 stores only tensors and plain Python containers (numpy arrays / scalars inside the RNG states, data cursors and
+aggregator states are converted on save and restored on load), so a checkpoint is read with
+``torch.load(weights_only=True)`` -- loading one cannot execute pickled code.  Files of the older formats need
+``BLADES_TRUST_CHECKPOINT=1`` (they are unpickled without that restriction).
 """
 from __future__ import annotations
 
@@ -27,7 +32,36 @@ import torch
 
 __all__ = ["save_checkpoint", "load_checkpoint", "FORMAT_VERSION"]
 
-FORMAT_VERSION = 2
+FORMAT_VERSION = 3
+_ND = "__ndarray__"
+
+
+def _to_plain(obj):
+    """numpy arrays / scalars -> tensors / Python scalars, recursively (tuples are kept as tagged lists)."""
+    if isinstance(obj, np.ndarray):
+        return {_ND: torch.from_numpy(np.ascontiguousarray(obj).copy()) if obj.dtype != np.uint32
+                else torch.from_numpy(obj.astype(np.int64)), "dtype": str(obj.dtype)}
+    if isinstance(obj, np.generic):
+        return obj.item()
+    if isinstance(obj, dict):
+        return {k: _to_plain(v) for k, v in obj.items()}
+    if isinstance(obj, tuple):
+        return {"__tuple__": [_to_plain(v) for v in obj]}
+    if isinstance(obj, list):
+        return [_to_plain(v) for v in obj]
+    return obj
+
+
+def _from_plain(obj):
+    if isinstance(obj, dict):
+        if _ND in obj:
+            return obj[_ND].numpy().astype(np.dtype(obj["dtype"]))
+        if "__tuple__" in obj and len(obj) == 1:
+            return tuple(_from_plain(v) for v in obj["__tuple__"])
+        return {k: _from_plain(v) for k, v in obj.items()}
+    if isinstance(obj, list):
+        return [_from_plain(v) for v in obj]
+    return obj
 
 
 def _rng_state(device: torch.device) -> dict:
@@ -69,9 +103,9 @@ def save_checkpoint(path: str, sim, server_sched=None, client_sched=None) -> Opt
         "client_lr": sim.client_lr,
         "schedulers": {"server": server_sched.state_dict() if server_sched else None,
                        "client": client_sched.state_dict() if client_sched else None},
-        "rng": rng_all,
-        "aggregator_state": agg.state_dict() if hasattr(agg, "state_dict") else {},
-        "data_cursors": _merged_cursors(sim),
+        "rng": _to_plain(rng_all),
+        "aggregator_state": _to_plain(agg.state_dict() if hasattr(agg, "state_dict") else {}),
+        "data_cursors": _to_plain(_merged_cursors(sim)),
         "config": {"n_clients": len(sim.get_clients()), "d": sim.engine.d,
                    "world_size": sim.world.size, "format_version": FORMAT_VERSION},
     }
@@ -87,8 +121,17 @@ def save_checkpoint(path: str, sim, server_sched=None, client_sched=None) -> Opt
 def load_checkpoint(path: str, sim, server_sched=None, client_sched=None) -> int:
     """Restore into a *prepared* simulator (``sim.prepare(model, ...)`` already called).
     Returns the last completed round."""
-    ck = torch.load(path, map_location="cpu", weights_only=False)
-    assert ck["config"]["format_version"] in (1, FORMAT_VERSION)
+    try:
+        ck = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception as e:                      # formats 1-2 pickle numpy objects
+        if os.environ.get("BLADES_TRUST_CHECKPOINT", "0") != "1":
+            raise RuntimeError(f"{path} is not a format-{FORMAT_VERSION} checkpoint (tensors and plain containers only); "
+                               "set BLADES_TRUST_CHECKPOINT=1 to unpickle an older, trusted file") from e
+        ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert ck["config"]["format_version"] in (1, 2, FORMAT_VERSION)
+    if ck["config"]["format_version"] >= 3:
+        for k in ("rng", "aggregator_state", "data_cursors"):
+            ck[k] = _from_plain(ck[k])
     model = sim.server.get_model()
     with torch.no_grad():
         own = model.state_dict()

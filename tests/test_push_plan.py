@@ -86,3 +86,25 @@ def test_pipeline_windows_are_contiguous_rounded_up_and_bounded(monkeypatch):
     assert all(w[0] % 128 == 0 for w in launched)
     cols = [w[3] for w in launched]
     assert cols == sorted(cols) and cols[0] == 0
+
+
+def test_checkpoint_plain_roundtrip_is_weights_only_loadable(tmp_path):
+    """Format-3 checkpoints hold tensors and plain containers only: numpy RNG states / cursors survive the conversion
+    and the file loads with ``weights_only=True`` (no code execution on resume)."""
+    import random
+    import torch
+    from blades_b200 import checkpoint as ck
+    rng = {"numpy": np.random.get_state(), "python": random.getstate(), "torch": torch.get_rng_state()}
+    cur = {"client_3": {"perm": np.arange(7)[::-1].copy(), "pos": np.int64(4), "epoch": 2, "f": np.float32(0.5)}}
+    payload = {"rng": ck._to_plain([rng]), "data_cursors": ck._to_plain(cur)}
+    path = tmp_path / "c.pt"
+    torch.save(payload, path)
+    back = torch.load(path, map_location="cpu", weights_only=True)
+    rng2 = ck._from_plain(back["rng"])[0]
+    cur2 = ck._from_plain(back["data_cursors"])
+    assert rng2["numpy"][0] == rng["numpy"][0] and (rng2["numpy"][1] == rng["numpy"][1]).all()
+    assert rng2["numpy"][1].dtype == np.uint32 and rng2["numpy"][2:] == rng["numpy"][2:]
+    assert rng2["python"] == rng["python"] and torch.equal(rng2["torch"], rng["torch"])
+    assert (cur2["client_3"]["perm"] == cur["client_3"]["perm"]).all() and cur2["client_3"]["pos"] == 4
+    np.random.set_state(rng2["numpy"])
+    random.setstate(rng2["python"])
