@@ -16,25 +16,27 @@ struct PoolParams {
     int NB, H, W, C, Ho, Wo, k, s, p;
 };
 
+// One block per output row (b, ho); threads run over (wo, channel quad) with 32-bit index arithmetic -- the flat
+// grid-stride form spent its time in 64-bit divisions (stem pooling: 100 us forward / 210 us backward against
+// 40 us of memory traffic).
 __global__ void __launch_bounds__(256)
 maxpool_nhwc_fwd_kernel(const __grid_constant__ PoolParams p) {
     const int c4 = p.C >> 2;
-    const long long total = (long long)p.NB * p.Ho * p.Wo * c4;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % c4) * 4;
-        long long t = i / c4;
-        const int wo = (int)(t % p.Wo); t /= p.Wo;
-        const int ho = (int)(t % p.Ho);
-        const long long b = t / p.Ho;
+    const unsigned ho = blockIdx.x % (unsigned)p.Ho;
+    const long long b = blockIdx.x / (unsigned)p.Ho;
+    const float* xb = p.x + b * p.H * p.W * p.C;
+    for (unsigned e = threadIdx.x; e < (unsigned)(p.Wo * c4); e += blockDim.x) {
+        const int wo = (int)(e / (unsigned)c4);
+        const int c = (int)(e - (unsigned)wo * (unsigned)c4) * 4;
         float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         int bx = -1, by = -1, bz = -1, bw = -1;
         for (int r = 0; r < p.k; ++r) {
-            const int h = ho * p.s - p.p + r;
+            const int h = (int)ho * p.s - p.p + r;
             if (h < 0 || h >= p.H) continue;
             for (int q = 0; q < p.k; ++q) {
                 const int w = wo * p.s - p.p + q;
                 if (w < 0 || w >= p.W) continue;
-                const float4 v = *reinterpret_cast<const float4*>(p.x + ((b * p.H + h) * p.W + w) * p.C + c);
+                const float4 v = *reinterpret_cast<const float4*>(xb + (h * p.W + w) * p.C + c);
                 const int pos = r * p.k + q;
                 // ATen's rule: start at the first window element; replace when larger or NaN
                 if (bx < 0 || v.x > best.x || v.x != v.x) { best.x = v.x; bx = pos; }
@@ -50,27 +52,29 @@ maxpool_nhwc_fwd_kernel(const __grid_constant__ PoolParams p) {
     }
 }
 
+// gather form (no atomics), one block per input row (b, h)
 __global__ void __launch_bounds__(256)
 maxpool_nhwc_bwd_kernel(const __grid_constant__ PoolParams p) {
     const int c4 = p.C >> 2;
-    const long long total = (long long)p.NB * p.H * p.W * c4;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % c4) * 4;
-        long long t = i / c4;
-        const int w = (int)(t % p.W); t /= p.W;
-        const int h = (int)(t % p.H);
-        const long long b = t / p.H;
+    const int h = (int)(blockIdx.x % (unsigned)p.H);
+    const long long b = blockIdx.x / (unsigned)p.H;
+    // output windows containing row h: ho*s - p <= h <= ho*s - p + k - 1   (uniform per block)
+    int ho0 = (h + p.p - p.k + 1 + p.s - 1); ho0 = ho0 < 0 ? 0 : ho0 / p.s;
+    const int ho1 = min((h + p.p) / p.s, p.Ho - 1);
+    const float* gb = p.x + b * p.Ho * p.Wo * p.C;
+    const unsigned char* ib = p.idx + b * p.Ho * p.Wo * p.C;
+    for (unsigned e = threadIdx.x; e < (unsigned)(p.W * c4); e += blockDim.x) {
+        const int w = (int)(e / (unsigned)c4);
+        const int c = (int)(e - (unsigned)w * (unsigned)c4) * 4;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        // output windows containing (h, w): ho*s - p <= h <= ho*s - p + k - 1
-        int ho0 = (h + p.p - p.k + 1 + p.s - 1); ho0 = ho0 < 0 ? 0 : ho0 / p.s;
         int wo0 = (w + p.p - p.k + 1 + p.s - 1); wo0 = wo0 < 0 ? 0 : wo0 / p.s;
-        const int ho1 = min((h + p.p) / p.s, p.Ho - 1), wo1 = min((w + p.p) / p.s, p.Wo - 1);
+        const int wo1 = min((w + p.p) / p.s, p.Wo - 1);
         for (int ho = ho0; ho <= ho1; ++ho)
             for (int wo = wo0; wo <= wo1; ++wo) {
                 const int pos = (h - (ho * p.s - p.p)) * p.k + (w - (wo * p.s - p.p));
-                const long long o = ((b * p.Ho + ho) * p.Wo + wo) * p.C + c;
-                const uchar4 id = *reinterpret_cast<const uchar4*>(p.idx + o);
-                const float4 g = *reinterpret_cast<const float4*>(p.x + o);
+                const int o = (ho * p.Wo + wo) * p.C + c;
+                const uchar4 id = *reinterpret_cast<const uchar4*>(ib + o);
+                const float4 g = *reinterpret_cast<const float4*>(gb + o);
                 if (id.x == pos) acc.x += g.x;
                 if (id.y == pos) acc.y += g.y;
                 if (id.z == pos) acc.z += g.z;
@@ -90,14 +94,18 @@ extern "C" int bl_maxpool_nhwc_fwd(const float* x, float* y, unsigned char* idx,
                                    int Wo, int k, int s, int pad, void* stream) {
     if (C % 4 != 0 || k * k > 255) return -1;
     PoolParams p{x, y, idx, NB, H, W, C, Ho, Wo, k, s, pad};
-    maxpool_nhwc_fwd_kernel<<<pool_grid((long long)NB * Ho * Wo * (C / 4)), 256, 0, (cudaStream_t)stream>>>(p);
+    if ((long long)NB * Ho > 0x7fffffffLL || (long long)H * W * C > 0x7fffffffLL) return -1;
+    const int tf = Wo * (C / 4);
+    maxpool_nhwc_fwd_kernel<<<(unsigned)(NB * Ho), tf >= 256 ? 256 : (tf + 31) / 32 * 32, 0, (cudaStream_t)stream>>>(p);
     return (int)cudaGetLastError();
 }
 extern "C" int bl_maxpool_nhwc_bwd(const float* gy, float* gx, const unsigned char* idx, int NB, int H, int W, int C,
                                    int Ho, int Wo, int k, int s, int pad, void* stream) {
     if (C % 4 != 0 || k * k > 255) return -1;
     PoolParams p{gy, gx, const_cast<unsigned char*>(idx), NB, H, W, C, Ho, Wo, k, s, pad};
-    maxpool_nhwc_bwd_kernel<<<pool_grid((long long)NB * H * W * (C / 4)), 256, 0, (cudaStream_t)stream>>>(p);
+    if ((long long)NB * H > 0x7fffffffLL || (long long)H * W * C > 0x7fffffffLL) return -1;
+    const int tb = W * (C / 4);
+    maxpool_nhwc_bwd_kernel<<<(unsigned)(NB * H), tb >= 256 ? 256 : (tb + 31) / 32 * 32, 0, (cudaStream_t)stream>>>(p);
     return (int)cudaGetLastError();
 }
 

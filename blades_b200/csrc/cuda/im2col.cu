@@ -130,6 +130,51 @@ im2col_nhwc_kernel(const __grid_constant__ Im2colNhwcParams p) {
     }
 }
 
+// (A float4-store variant for scalar-channel wide rows -- the 7x7 stem, Cin = 3, K = 147 -- with the tap offsets in a
+// shared-memory table measured SLOWER than the element-per-thread kernel above: 280 vs 221 us; removed.)
+// Narrow rows (ldk <= 32: the stem, K = 3 * 3 * 3 = 27 -> 28): a lane is a column, a warp walks 32 rows at a time.
+// Each lane decodes ONE of those rows (the divisions), the decoded (image base, h0, w0) travel by shuffle, and every
+// store instruction writes one whole row contiguously.  The general kernel keeps 28 of its 256 threads busy on this
+// shape: 222 us for 92 MB of output (stem, 3200 x 32 x 32 inputs); this form is bound by the stores.
+__global__ void __launch_bounds__(256)
+im2col_nhwc_narrow_kernel(const __grid_constant__ Im2colNhwcParams p) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int col = lane;
+    const bool live = col < p.ldk;
+    const bool pad = col >= p.K;
+    const int tap = pad ? 0 : col / p.Cin;
+    const int cin = pad ? 0 : col - tap * p.Cin;
+    const int r = tap / p.kw, sq = tap - r * p.kw;
+    const int dh = r * p.dh, dw = sq * p.dw;
+    const int L = p.Ho * p.Wo;
+    for (long long row_base = warp * 32; row_base < p.rows; row_base += nwarps * 32) {
+        const long long row = row_base + lane;
+        long long base = -1;
+        int h0 = 0, w0 = 0;
+        if (row < p.rows) {
+            const long long b = row / L;
+            const int l = (int)(row - b * L);
+            const int ho = l / p.Wo, wo = l - ho * p.Wo;
+            base = b * p.sb;
+            h0 = ho * p.sh_ - p.ph;
+            w0 = wo * p.sw_ - p.pw;
+        }
+        const int n_here = (int)min((long long)32, p.rows - row_base);
+#pragma unroll 4
+        for (int i = 0; i < n_here; ++i) {
+            const long long bi = __shfl_sync(0xffffffffu, base, i);
+            const int h = __shfl_sync(0xffffffffu, h0, i) + dh, w = __shfl_sync(0xffffffffu, w0, i) + dw;
+            if (live) {
+                float v = 0.f;
+                if (!pad && h >= 0 && h < p.H && w >= 0 && w < p.W) v = __ldg(p.x + bi + h * p.sh + w * p.sw + cin * p.sc);
+                p.out[(row_base + i) * p.ldk + col] = v;
+            }
+        }
+    }
+}
+
 extern "C" int bl_im2col_nhwc(const float* x, float* out, int NB, int Cin, int H, int W, int kh, int kw, int sh,
                               int sw, int ph, int pw, int dh, int dw, int Ho, int Wo, int ldk, long long xsb,
                               long long xsh, long long xsw, long long xsc, void* stream) {
@@ -142,6 +187,10 @@ extern "C" int bl_im2col_nhwc(const float* x, float* out, int NB, int Cin, int H
     const bool vec = (Cin % 4 == 0) && (ldk % 4 == 0) && (((uintptr_t)x) % 16 == 0) && (((uintptr_t)out) % 16 == 0) &&
                      xsc == 1 && xsw % 4 == 0 && xsh % 4 == 0 && xsb % 4 == 0;
     if (vec) im2col_nhwc_kernel<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
-    else im2col_nhwc_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    else if (ldk <= 32) {
+        long long g = (p.rows + 255) / 256;              // 8 warps x 32 rows per block and pass
+        if (g > 148LL * 16) g = 148LL * 16;
+        im2col_nhwc_narrow_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(p);
+    } else im2col_nhwc_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
     return (int)cudaGetLastError();
 }

@@ -307,7 +307,10 @@ def test_client_bn_kernels(n, B, C, H):
 
 
 @pytest.mark.parametrize("shape", [(6, 3, 32, 32, 7, 2, 3), (8, 64, 8, 8, 3, 1, 1), (4, 128, 4, 4, 3, 2, 1),
-                                   (4, 256, 2, 2, 1, 2, 0), (5, 512, 1, 1, 3, 1, 1), (3, 6, 9, 7, 3, 1, 0)])
+                                   (4, 256, 2, 2, 1, 2, 0), (5, 512, 1, 1, 3, 1, 1), (3, 6, 9, 7, 3, 1, 0),
+                                   # narrow rows (K <= 32: warp-per-32-rows kernel): the stem shape, ragged row counts
+                                   (5, 3, 32, 32, 3, 1, 1), (3, 3, 7, 5, 3, 1, 1), (2, 2, 5, 5, 2, 1, 0), (1, 1, 3, 3, 3, 1, 1),
+                                   (70, 3, 8, 8, 3, 2, 1)])
 def test_im2col_nhwc(shape):
     import torch.nn.functional as F
     from blades_b200.ops.im2col import im2col_nhwc
