@@ -27,6 +27,11 @@ class Autogm(_BaseAggregator):
         return self.gm_agg._geometric_median_objective(median, points, alphas)
 
     def aggregate(self, matrix, weights=None):
+        dg = matrix.gram_device()
+        if dg is not None:               # water filling + Weiszfeld on the device (csrc/cuda/gram_solve.cu): no host sync
+            from ..ops import gram_solve
+            return matrix.combine(gram_solve.autogm_weights(dg, self.lamb, self.maxiter, self.eps, self.ftol,
+                                                            self.compat, self.compat))
         w = gops.autogm_weights(matrix.gram(), self.lamb, self.maxiter, self.eps, self.ftol,
                                 sort_by_index=self.compat, compounding=self.compat)
         return matrix.combine(w)

@@ -38,6 +38,17 @@ struct ClientBNParams {
 __device__ __forceinline__ float4 bn_relu_mask(float4 g, float4 a) {
     return make_float4(a.x > 0.f ? g.x : 0.f, a.y > 0.f ? g.y : 0.f, a.z > 0.f ? g.z : 0.f, a.w > 0.f ? g.w : 0.f);
 }
+// y_pre = x * (gamma * rstd) + (beta - mean * gamma * rstd): ONE definition shared by the forward kernels and by the
+// backward kernels that recompute the ReLU mask from x instead of reading the forward output (same expressions ->
+// same contraction -> bit-identical y_pre, so (y_pre > 0) is exactly (act > 0) whenever no residual was added).
+__device__ __forceinline__ void bn_affine(const float4 ga, const float4 be, const float4 mean, const float4 rstd,
+                                          float4& g, float4& sh) {
+    g = make_float4(ga.x * rstd.x, ga.y * rstd.y, ga.z * rstd.z, ga.w * rstd.w);
+    sh = make_float4(be.x - mean.x * g.x, be.y - mean.y * g.y, be.z - mean.z * g.z, be.w - mean.w * g.w);
+}
+__device__ __forceinline__ float4 bn_pre(const float4 v, const float4 g, const float4 sh) {
+    return make_float4(fmaf(v.x, g.x, sh.x), fmaf(v.y, g.y, sh.y), fmaf(v.z, g.z, sh.z), fmaf(v.w, g.w, sh.w));
+}
 __device__ __forceinline__ float4 bn_act(float4 o, const float4* res, long long idx, int relu) {
     if (res != nullptr) { const float4 r = res[idx]; o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
@@ -203,15 +214,14 @@ client_bn_nhwc_fwd_kernel(const __grid_constant__ ClientBNParams p) {
                                         rsqrtf(var.z / m + p.eps), rsqrtf(var.w / m + p.eps));
         const float4 ga = *reinterpret_cast<const float4*>(p.gamma + ch);
         const float4 be = *reinterpret_cast<const float4*>(p.beta + ch);
-        const float4 g = make_float4(ga.x * rstd.x, ga.y * rstd.y, ga.z * rstd.z, ga.w * rstd.w);
-        const float4 sh = make_float4(be.x - mean.x * g.x, be.y - mean.y * g.y, be.z - mean.z * g.z, be.w - mean.w * g.w);
+        float4 g, sh;
+        bn_affine(ga, be, mean, rstd, g, sh);
         float4* yb = reinterpret_cast<float4*>(p.y + (long long)c * R * p.C + ch);
         const float4* rb = p.res ? reinterpret_cast<const float4*>(p.res + (long long)c * R * p.C + ch) : nullptr;
 #pragma unroll 4
         for (int r = rg; r < R; r += kBnGroups) {
             const float4 v = xb[(long long)r * rs];
-            yb[(long long)r * rs] = bn_act(make_float4(fmaf(v.x, g.x, sh.x), fmaf(v.y, g.y, sh.y), fmaf(v.z, g.z, sh.z),
-                                                       fmaf(v.w, g.w, sh.w)), rb, (long long)r * rs, p.relu);
+            yb[(long long)r * rs] = bn_act(bn_pre(v, g, sh), rb, (long long)r * rs, p.relu);
         }
         if (rg == 0) {
             *reinterpret_cast<float4*>(p.mean + c * p.C + ch) = mean;
@@ -239,13 +249,19 @@ client_bn_nhwc_bwd_kernel(const __grid_constant__ ClientBNParams p) {
         mean = *reinterpret_cast<const float4*>(p.mean + c * p.C + ch);
         rstd = *reinterpret_cast<const float4*>(p.rstd + c * p.C + ch);
     }
+    // ReLU mask: from the forward output `act`, or -- act == nullptr, unit without a residual -- recomputed from x
+    const bool remask = p.relu && p.act == nullptr;
+    float4 fg = make_float4(0.f, 0.f, 0.f, 0.f), fsh = fg;
+    if (live && remask)
+        bn_affine(*reinterpret_cast<const float4*>(p.gamma + ch), *reinterpret_cast<const float4*>(p.beta + ch), mean, rstd,
+                  fg, fsh);
     float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sg = sb;
     if (live) {
 #pragma unroll 4
         for (int r = rg; r < R; r += kBnGroups) {
             float4 g = gb[(long long)r * rs];
             const float4 v = xb[(long long)r * rs];
-            if (p.relu) g = bn_relu_mask(g, ab[(long long)r * rs]);
+            if (p.relu) g = bn_relu_mask(g, remask ? bn_pre(v, fg, fsh) : ab[(long long)r * rs]);
             if (mb != nullptr) mb[(long long)r * rs] = g;
             sb.x += g.x; sb.y += g.y; sb.z += g.z; sb.w += g.w;
             sg.x = fmaf(g.x, (v.x - mean.x) * rstd.x, sg.x);
@@ -274,7 +290,7 @@ client_bn_nhwc_bwd_kernel(const __grid_constant__ ClientBNParams p) {
             for (int r = rg; r < R; r += kBnGroups) {
                 float4 g = gb[(long long)r * rs];
                 const float4 v = xb[(long long)r * rs];
-                if (p.relu) g = bn_relu_mask(g, ab[(long long)r * rs]);     // idempotent if gmask aliased gy
+                if (p.relu) g = bn_relu_mask(g, remask ? bn_pre(v, fg, fsh) : ab[(long long)r * rs]);   // idempotent if gmask aliased gy
                 float4 o;
                 o.x = k.x * (g.x - (dbeta.x + (v.x - mean.x) * rstd.x * dgamma.x) * inv_m);
                 o.y = k.y * (g.y - (dbeta.y + (v.y - mean.y) * rstd.y * dgamma.y) * inv_m);
@@ -375,15 +391,14 @@ client_bn_nhwc_fwd_cl_kernel(const __grid_constant__ ClientBNParams p) {
                                         rsqrtf(var.z / m + p.eps), rsqrtf(var.w / m + p.eps));
         const float4 ga = *reinterpret_cast<const float4*>(p.gamma + ch);
         const float4 be = *reinterpret_cast<const float4*>(p.beta + ch);
-        const float4 g = make_float4(ga.x * rstd.x, ga.y * rstd.y, ga.z * rstd.z, ga.w * rstd.w);
-        const float4 sh = make_float4(be.x - mean.x * g.x, be.y - mean.y * g.y, be.z - mean.z * g.z, be.w - mean.w * g.w);
+        float4 g, sh;
+        bn_affine(ga, be, mean, rstd, g, sh);
         float4* yb = reinterpret_cast<float4*>(p.y + base);
         const float4* rb = p.res ? reinterpret_cast<const float4*>(p.res + base) : nullptr;
 #pragma unroll 8
         for (int r = rg; r < Rc; r += GROUPS) {
             const float4 v = bn_tile[r * QUADS + q];
-            yb[(long long)r * rs] = bn_act(make_float4(fmaf(v.x, g.x, sh.x), fmaf(v.y, g.y, sh.y), fmaf(v.z, g.z, sh.z),
-                                                       fmaf(v.w, g.w, sh.w)), rb, (long long)r * rs, p.relu);
+            yb[(long long)r * rs] = bn_act(bn_pre(v, g, sh), rb, (long long)r * rs, p.relu);
         }
         if (rg == 0 && rank == 0) {
             *reinterpret_cast<float4*>(p.mean + c * p.C + ch) = mean;
@@ -420,13 +435,18 @@ client_bn_nhwc_bwd_cl_kernel(const __grid_constant__ ClientBNParams p) {
         mean = *reinterpret_cast<const float4*>(p.mean + c * p.C + ch);
         rstd = *reinterpret_cast<const float4*>(p.rstd + c * p.C + ch);
     }
+    const bool remask = p.relu && p.act == nullptr;
+    float4 fg = make_float4(0.f, 0.f, 0.f, 0.f), fsh = fg;
+    if (live && remask)
+        bn_affine(*reinterpret_cast<const float4*>(p.gamma + ch), *reinterpret_cast<const float4*>(p.beta + ch), mean, rstd,
+                  fg, fsh);
     float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sg = sb;
     if (live) {
 #pragma unroll 4
         for (int r = rg; r < Rc; r += GROUPS) {
             float4 g = __ldcs(&gb[(long long)r * rs]);
             const float4 v = __ldcs(&xb[(long long)r * rs]);
-            if (p.relu) g = bn_relu_mask(g, __ldcs(&ab[(long long)r * rs]));
+            if (p.relu) g = bn_relu_mask(g, remask ? bn_pre(v, fg, fsh) : __ldcs(&ab[(long long)r * rs]));
             if (mb != nullptr) mb[(long long)r * rs] = g;
             const float4 xh = make_float4((v.x - mean.x) * rstd.x, (v.y - mean.y) * rstd.y, (v.z - mean.z) * rstd.z,
                                           (v.w - mean.w) * rstd.w);

@@ -122,7 +122,7 @@ extern "C" int bl_sizeof_krum_params() { return (int)sizeof(KrumParams); }
 struct IterParams {
     const float* G; const int* idx; int ld;
     int n;                   // Gram rows (centered clipping: n clients + 1 momentum row)
-    int kind;                // 0 Weiszfeld, 1 centered clipping
+    int kind;                // 0 Weiszfeld, 1 centered clipping, 2 AutoGM (Weiszfeld inside a water-filling loop)
     int maxiter;             // Weiszfeld: max iterations; centered clipping: n_iter
     int compounding;         // Weiszfeld quirk Q5: new weights derive from the previous weights
     double eps, ftol, tau;
@@ -131,6 +131,9 @@ struct IterParams {
     int use_smem;            // launcher: n*n floats fit in dynamic shared memory
     float* w;                // [n] out (centered clipping: coefficients over [u_0..u_{n-2}, m_prev])
     int* iters;              // out: Weiszfeld iterations taken
+    double lamb;             // AutoGM regulariser
+    int sort_by_index;       // AutoGM quirk Q6: the water-filling visits the clients in index order
+    int pad_;
 };
 
 // dist_j = || sum_i w_i u_i - u_j ||  from the Gram matrix:  sqrt(max(w^T G w - 2 (G w)_j + G_jj, 0))
@@ -141,6 +144,35 @@ __device__ double dist_to_combo(const float* gs, int n, const double* w, int j, 
     const double wgw = block_sum(j < n ? w[j] * gw : 0.0, red);
     if (j >= n) return 0.0;
     return sqrt(fmax(wgw - 2.0 * gw + (double)gs[(long long)j * n + j], 0.0));
+}
+
+// Weiszfeld iterations for point weights `alpha` (one per thread); leaves the weights in w[], returns this thread's
+// distance to the final iterate and the iteration count.  Mirrors selectors.cpp::weiszfeld statement for statement.
+__device__ int weiszfeld_run(const float* gs, int n, int j, double alpha, const IterParams& p, double* w, double* red,
+                             double& dist_out) {
+    double run = alpha;
+    __syncthreads();
+    if (j <= BL_MAX_ROWS) w[j] = j < n ? 1.0 / n : 0.0;                 // start at the plain mean (geomed.py:66)
+    __syncthreads();
+    double dist = dist_to_combo(gs, n, w, j, red);
+    double obj = block_sum(j < n ? run * dist : 0.0, red);
+    int it = 0;
+    for (it = 1; it <= p.maxiter; ++it) {
+        const double prev = obj;
+        const double base = p.compounding ? run : alpha;
+        double nw = j < n ? fmax(p.eps, base / fmax(p.eps, dist)) : 0.0;
+        const double sum = block_sum(nw, red);
+        nw /= sum;
+        run = nw;
+        __syncthreads();
+        if (j < n) w[j] = nw;
+        __syncthreads();
+        dist = dist_to_combo(gs, n, w, j, red);
+        obj = block_sum(j < n ? run * dist : 0.0, red);
+        if (fabs(prev - obj) < p.ftol * obj) break;                      // uniform: obj is a broadcast value
+    }
+    dist_out = dist;
+    return min(it, p.maxiter);
 }
 
 __global__ void __launch_bounds__(kSolveThreads)
@@ -156,28 +188,52 @@ gram_iter_kernel(const __grid_constant__ IterParams p) {
 
     if (p.kind == 0) {
         const double alpha = j < n ? (p.alphas ? (double)p.alphas[j] : 1.0 / n) : 0.0;
-        double run = alpha;
-        if (j <= BL_MAX_ROWS) w[j] = j < n ? 1.0 / n : 0.0;             // start at the plain mean (geomed.py:66)
-        __syncthreads();
-        double dist = dist_to_combo(gs, n, w, j, red);
-        double obj = block_sum(run * dist, red);
-        int it = 0;
-        for (it = 1; it <= p.maxiter; ++it) {
-            const double prev = obj;
-            const double base = p.compounding ? run : alpha;
-            double nw = j < n ? fmax(p.eps, base / fmax(p.eps, dist)) : 0.0;
-            const double sum = block_sum(nw, red);
-            nw /= sum;
-            run = nw;
+        double dist;
+        const int it = weiszfeld_run(gs, n, j, alpha, p, w, red, dist);
+        if (j < n) p.w[j] = (float)w[j];
+        if (j == 0 && p.iters) *p.iters = it;
+    } else if (p.kind == 2) {
+        // AutoGM (reference autogm.py:36-65, host twin selectors.cpp::bl_autogm): alternate a weighted geometric median
+        // with the water-filling update alpha = max(eta - dist, 0) / lambda; the serial prefix scan of the water
+        // filling (n <= 512 steps) runs on thread 0 over shared memory
+        __shared__ double s_dist[BL_MAX_ROWS];
+        __shared__ int s_order[BL_MAX_ROWS];
+        __shared__ double s_eta;
+        double alpha = j < n ? 1.0 / n : 0.0, dist;
+        weiszfeld_run(gs, n, j, alpha, p, w, red, dist);
+        double glob = block_sum(j < n ? alpha * dist : 0.0, red) + p.lamb * block_sum(alpha * alpha, red) / 2.0;
+        for (int iter = 0; iter < p.maxiter; ++iter) {
+            const double prev = glob;
             __syncthreads();
-            if (j < n) w[j] = nw;
+            if (j < n) s_dist[j] = dist;
             __syncthreads();
-            dist = dist_to_combo(gs, n, w, j, red);
-            obj = block_sum(j < n ? run * dist : 0.0, red);
-            if (fabs(prev - obj) < p.ftol * obj) break;                  // uniform: obj is a broadcast value
+            if (j < n) {
+                int rank = j;
+                if (!p.sort_by_index) {                                    // stable argsort of the distances
+                    rank = 0;
+                    for (int l = 0; l < n; ++l) rank += (s_dist[l] < dist || (s_dist[l] == dist && l < j)) ? 1 : 0;
+                }
+                s_order[rank] = j;
+            }
+            __syncthreads();
+            if (j == 0) {
+                double eta_opt = 1e16, csum = 0.0;
+                for (int q = 0; q < n; ++q) {
+                    const double dq = s_dist[s_order[q]];
+                    csum += dq;
+                    const double eta = (csum + p.lamb) / (q + 1);
+                    if (eta - dq < 0) break;
+                    eta_opt = eta;
+                }
+                s_eta = eta_opt;
+            }
+            __syncthreads();
+            alpha = j < n ? fmax(s_eta - dist, 0.0) / p.lamb : 0.0;
+            weiszfeld_run(gs, n, j, alpha, p, w, red, dist);
+            glob = block_sum(j < n ? alpha * dist : 0.0, red) + p.lamb * block_sum(alpha * alpha, red) / 2.0;
+            if (fabs(prev - glob) < p.ftol * glob) break;
         }
         if (j < n) p.w[j] = (float)w[j];
-        if (j == 0 && p.iters) *p.iters = min(it, p.maxiter);
     } else {
         const int nc = n - 1;                                            // clients; row nc is the previous momentum
         if (j <= BL_MAX_ROWS) w[j] = (j == nc) ? 1.0 : 0.0;

@@ -63,7 +63,7 @@ def supports_eval(model: nn.Module, x: torch.Tensor) -> bool:
 
 class _Unit:
     """conv -> per-client BN (+ residual) (+ ReLU): the tensors the backward pass needs."""
-    __slots__ = ("conv", "bn", "wname", "gname", "bname", "x", "c", "mean", "rstd", "y", "relu", "cols", "w2d")
+    __slots__ = ("conv", "bn", "wname", "gname", "bname", "x", "c", "mean", "rstd", "y", "relu", "cols", "w2d", "has_res")
 
 
 def _w2d(conv: nn.Conv2d) -> torch.Tensor:
@@ -113,6 +113,7 @@ class _Pass:
                  res: Optional[torch.Tensor] = None) -> _Unit:
         u = _Unit()
         u.conv, u.bn, u.relu = conv, bn, relu
+        u.has_res = res is not None
         u.wname = self.names[id(conv)] + ".weight"
         u.gname, u.bname = self.names[id(bn)] + ".weight", self.names[id(bn)] + ".bias"
         u.c = self.conv_fwd(u, x)
@@ -129,7 +130,8 @@ class _Pass:
         s = self.sink
         assert gy.is_contiguous(memory_format=torch.channels_last)      # the in-place mask must hit the caller's tensor
         gc = kbn.backward(gy, u.c, u.mean, u.rstd, u.bn.weight.data, self.n, s.view(u.gname), s.view(u.bname), s.alpha,
-                          True, act=u.y if u.relu else None, gmask=gy if (want_masked and u.relu) else None, nhwc=True)
+                          True, act=u.y if u.relu else None, gmask=gy if (want_masked and u.relu) else None, nhwc=True,
+                          beta=None if u.has_res else u.bn.bias.data)
         s.written.update((u.gname, u.bname))
         return gc
 

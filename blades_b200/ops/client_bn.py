@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -40,6 +41,10 @@ def _same_layout(a: torch.Tensor, x: torch.Tensor) -> bool:
         and x.is_contiguous(memory_format=cl)
 
 
+#: BLADES_BN_REMASK=0: always read the forward output for the ReLU mask
+_REMASK = os.environ.get("BLADES_BN_REMASK", "1") != "0"
+
+
 def _lib():
     global _checked
     lib = _loader.cuda_lib()
@@ -76,11 +81,13 @@ def forward(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, n: int, ep
 
 def backward(gy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor,
              n: int, dgamma_view: torch.Tensor, dbeta_view: torch.Tensor, alpha: float, need_dx: bool,
-             act: Optional[torch.Tensor] = None, gmask: Optional[torch.Tensor] = None, nhwc: Optional[bool] = None
-             ) -> Optional[torch.Tensor]:
+             act: Optional[torch.Tensor] = None, gmask: Optional[torch.Tensor] = None, nhwc: Optional[bool] = None,
+             beta: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
     """``dgamma_view`` / ``dbeta_view``: strided ``[n, C]`` windows of the update matrix (row stride ld).
     ``act`` (NHWC only): the forward OUTPUT of a fused ReLU -- the incoming gradient is masked with ``act > 0``
-    first; ``gmask`` (may be ``gy`` itself) receives that masked gradient (what a residual branch needs)."""
+    first; ``gmask`` (may be ``gy`` itself) receives that masked gradient (what a residual branch needs).
+    ``beta`` (NHWC, with ``act``): the unit had NO residual input, so the kernel recomputes the pre-activation from
+    ``x`` (bit-identical to the forward pass) for the mask instead of reading ``act`` -- one tensor less to stream."""
     NB, Cc, H, W = x.shape
     nhwc = is_nhwc(x) if nhwc is None else nhwc
     assert nhwc or (act is None and gmask is None)
@@ -95,6 +102,9 @@ def backward(gy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.
     if act is not None:
         assert _same_layout(act, x)
         p.act, p.relu = act.data_ptr(), 1
+        if beta is not None and nhwc and _REMASK:
+            beta = beta if beta.data_ptr() % 16 == 0 else beta.clone()
+            p.beta, p.act = beta.data_ptr(), None
     if gmask is not None:
         assert _same_layout(gmask, x)
         p.gmask = gmask.data_ptr()

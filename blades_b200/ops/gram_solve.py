@@ -12,7 +12,8 @@ import torch
 
 from . import _loader
 
-__all__ = ["DeviceGram", "enabled", "krum_weights", "weiszfeld_weights", "centered_clip_coeffs", "fltrust_weights"]
+__all__ = ["DeviceGram", "enabled", "krum_weights", "weiszfeld_weights", "centered_clip_coeffs", "fltrust_weights",
+           "autogm_weights"]
 
 
 def enabled() -> bool:
@@ -44,7 +45,8 @@ class IterParams(C.Structure):
     _fields_ = [("G", C.c_void_p), ("idx", C.c_void_p), ("ld", C.c_int), ("n", C.c_int), ("kind", C.c_int),
                 ("maxiter", C.c_int), ("compounding", C.c_int), ("eps", C.c_double), ("ftol", C.c_double),
                 ("tau", C.c_double), ("alphas", C.c_void_p), ("gs", C.c_void_p), ("use_smem", C.c_int),
-                ("w", C.c_void_p), ("iters", C.c_void_p)]
+                ("w", C.c_void_p), ("iters", C.c_void_p), ("lamb", C.c_double), ("sort_by_index", C.c_int),
+                ("pad_", C.c_int)]
 
 
 class TrustParams(C.Structure):
@@ -101,7 +103,8 @@ def krum_weights(dg: DeviceGram, n: int, f: int, m: int, squared_twice: bool, va
 
 
 def _iter(dg: DeviceGram, kind: int, maxiter: int, compounding: bool, eps: float, ftol: float, tau: float,
-          alphas: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+          alphas: Optional[torch.Tensor], lamb: float = 0.0, sort_by_index: bool = True
+          ) -> Tuple[torch.Tensor, torch.Tensor]:
     lib = _lib()
     dev = dg.G.device
     sc = _scratch(dev)
@@ -112,6 +115,7 @@ def _iter(dg: DeviceGram, kind: int, maxiter: int, compounding: bool, eps: float
     p.G, p.idx, p.ld, p.n, p.kind = dg.G.data_ptr(), dg.idx.data_ptr(), dg.G.stride(0), n, kind
     p.maxiter, p.compounding = int(maxiter), int(bool(compounding))
     p.eps, p.ftol, p.tau = float(eps), float(ftol), float(tau)
+    p.lamb, p.sort_by_index = float(lamb), int(bool(sort_by_index))
     p.alphas = alphas.data_ptr() if alphas is not None else None
     if n * n * 4 > 200 * 1024:
         if sc["gs"] is None or sc["gs"].numel() < n * n:
@@ -131,6 +135,13 @@ def weiszfeld_weights(dg: DeviceGram, alphas, maxiter: int, eps: float, ftol: fl
         a = torch.as_tensor(alphas, dtype=torch.float32).to(dg.G.device).contiguous()
         assert a.numel() == dg.n
     return _iter(dg, 0, maxiter, compounding, eps, ftol, 0.0, a)
+
+
+def autogm_weights(dg: DeviceGram, lamb: Optional[float], maxiter: int, eps: float, ftol: float, sort_by_index: bool,
+                   compounding: bool) -> torch.Tensor:
+    """AutoGM weights (Weiszfeld inside the water-filling loop), one launch; ``lamb`` defaults to the row count."""
+    return _iter(dg, 2, maxiter, compounding, eps, ftol, 0.0, None, lamb=float(dg.n if lamb is None else lamb),
+                 sort_by_index=sort_by_index)[0]
 
 
 def centered_clip_coeffs(dg: DeviceGram, tau: float, n_iter: int) -> torch.Tensor:

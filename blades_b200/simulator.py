@@ -356,7 +356,7 @@ class Simulator(object):
     def _static_round_possible(self, local_steps: int) -> bool:
         """The round is a fixed sequence of device work (no host decisions): fedsgd on the batched engine,
         attack fused as virtual rows (or none), coordinate-wise built-in aggregator, fused SGD server step."""
-        from .aggregators import Centeredclipping, Fltrust, Geomed, Krum, Mean, Median, Multikrum, Trimmedmean
+        from .aggregators import Autogm, Centeredclipping, Fltrust, Geomed, Krum, Mean, Median, Multikrum, Trimmedmean
         eng = self.engine
         if local_steps != 1 or eng.device.type != "cuda" or eng.timer.enabled or not self._opts["fuse_server_step"]:
             return False
@@ -364,7 +364,7 @@ class Simulator(object):
         # Gram-based aggregators whose solver runs on the device (ops/gram_solve) are a fixed sequence of launches too:
         # Gram pass -> (in-switch reduce) -> solver -> combine with device-resident weights
         from .ops import gram_solve
-        devsolve = type(self.aggregator) in (Krum, Multikrum, Geomed, Centeredclipping, Fltrust) and gram_solve.enabled() \
+        devsolve = type(self.aggregator) in (Krum, Multikrum, Geomed, Autogm, Centeredclipping, Fltrust) and gram_solve.enabled() \
             and eng.use_kernels
         eng.agg_windows_ok = coordwise          # only coordinate-wise aggregators can be pipelined window by window
         if not (coordwise or devsolve) or not self.server._flat_fast_path_ok():
@@ -602,8 +602,11 @@ class Simulator(object):
             checkpoint_path: Optional[str] = None,
             checkpoint_interval: int = 0,
     ):
-        """Run the adversarial training; returns the list of per-round wall-clock seconds
-        (device-synchronised, unlike the reference)."""
+        """Run the adversarial training; returns the list of per-round seconds.  On CUDA the rounds are timed with CUDA
+        events on the round stream (completion of round r-1 to completion of round r) and the host does NOT wait for
+        the device after every round: it issues round r+1 (batch indices, graph launch) while round r still runs, so
+        no launch gap opens between rounds (the reference reports host wall clock per round without any device
+        synchronisation, simulator.py:330-360).  Validation rounds, checkpoints and the end of the run synchronise."""
         self.prepare(model, server_optimizer, client_optimizer, loss, server_lr, client_lr,
                      reset_weights=resume is None)
         self.engine.track_cursors = bool(checkpoint_path and checkpoint_interval)
@@ -614,6 +617,17 @@ class Simulator(object):
             client_lr = self.client_lr
         global_start = time()
         ret = []
+        on_cuda = self.device.type == "cuda"
+        marks = []                      # CUDA events at round boundaries (on_cuda): marks[i] .. marks[i+1] = one round
+
+        def _flush_marks():
+            if len(marks) > 1:
+                marks[-1].synchronize()
+                ret.extend(marks[i].elapsed_time(marks[i + 1]) / 1e3 for i in range(len(marks) - 1))
+                del marks[:-1]
+        if on_cuda:
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[0].record(torch.cuda.current_stream(self.device))
         show = self._opts["progress"] and self.world.rank == 0
         bar = _progress(global_rounds, show) if start_round == 1 else _NullBar(range(start_round, global_rounds + 1))
         with bar as t:
@@ -638,16 +652,24 @@ class Simulator(object):
                         warnings.filterwarnings("ignore", message="Detected call of `lr_scheduler.step\\(\\)` before")
                         client_lr_scheduler.step()
                     client_lr = client_lr_scheduler.get_last_lr()[0]
-                if self.device.type == "cuda":
-                    torch.cuda.synchronize(self.device)
-                ret.append(time() - round_start)
+                if on_cuda:
+                    marks.append(torch.cuda.Event(enable_timing=True))
+                    marks[-1].record(torch.cuda.current_stream(self.device))
+                    if len(marks) > 256:
+                        _flush_marks()
+                else:
+                    ret.append(time() - round_start)
                 self.debug_logger.info(
                     f"E={rnd}; Client learning rate = {client_lr:}; Time cost = {time() - global_start}")
                 if checkpoint_path and checkpoint_interval and rnd % checkpoint_interval == 0:
+                    _flush_marks()
                     from .checkpoint import save_checkpoint
                     self.client_lr = client_lr
                     save_checkpoint(checkpoint_path, self, server_lr_scheduler, client_lr_scheduler)
         self.client_lr = client_lr
+        _flush_marks()
+        if on_cuda:
+            torch.cuda.synchronize(self.device)
         self.engine.finish()          # rewind batches prefetched for a round that will not happen
         return ret
 

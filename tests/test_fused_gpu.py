@@ -96,8 +96,11 @@ def test_client_bn_fused_relu_residual(n, B, C, H, with_res):
     (gx_ref,) = torch.autograd.grad(pre, x5, gmasked_ref)
     U = torch.zeros(n, 2 * C + 64, device=_dev())
     g_inplace = gy.clone(memory_format=torch.channels_last)
+    # without a residual the kernel is told beta and recomputes the ReLU mask from x (no read of the forward output):
+    # the masked gradient must be EXACTLY the one the act-based mask gives
     dx = kbn.backward(g_inplace, x, mean, rstd, gamma, n, U[:, 8:8 + C], U[:, 8 + C:8 + 2 * C], -0.1, True, act=y,
-                      gmask=g_inplace, nhwc=True)
+                      gmask=g_inplace, nhwc=True, beta=None if with_res else beta)
+    assert torch.equal(g_inplace, gy * (y > 0))                                              # bit-identical mask
     assert torch.allclose(g_inplace.double().view_as(yref), gmasked_ref, atol=1e-6)         # residual branch's share
     assert torch.allclose(dx.double().view_as(gx_ref), gx_ref, atol=2e-4, rtol=1e-3)
     assert torch.allclose(U[:, 8:8 + C].double(), -0.1 * (gmasked_ref * xhat).sum((1, 3)), atol=2e-3, rtol=1e-3)

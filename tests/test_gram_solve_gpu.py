@@ -51,6 +51,19 @@ def test_device_weiszfeld_matches_host(n, compounding, maxiter):
     assert abs(int(it.item()) - it_h) <= 1          # the stopping test sits at 1e-10 relative: fp64 summation order
 
 
+@pytest.mark.parametrize("n,by_index,compounding,lamb", [(10, True, True, None), (40, False, False, 3.0), (100, True, True, None),
+                                                         (100, False, True, 20.0), (300, True, False, None)])
+def test_device_autogm_matches_host(n, by_index, compounding, lamb):
+    from blades_b200.aggregators import _gramops as gops
+    from blades_b200.ops import gram_solve
+    u = _matrix(n, 8192, 13 * n, outliers=n // 5)
+    dg = _dg(u)
+    G = dg.dense().double().cpu().numpy()
+    want = gops.autogm_weights(G, lamb, 30, 1e-6, 1e-10, sort_by_index=by_index, compounding=compounding)
+    w = gram_solve.autogm_weights(dg, lamb, 30, 1e-6, 1e-10, by_index, compounding).cpu().numpy()
+    np.testing.assert_allclose(w, want, rtol=5e-4, atol=1e-7)
+
+
 @pytest.mark.parametrize("n,tau,iters", [(10, 10.0, 5), (100, 0.05, 5), (100, 1e-3, 1), (300, 0.5, 3)])
 def test_device_centered_clip_matches_host(n, tau, iters):
     from blades_b200.aggregators import _gramops as gops
@@ -97,7 +110,7 @@ def test_combine_reads_device_weights_and_skips_zero_rows():
                                       ("multikrum", dict(num_byzantine=6)),
                                       ("geomed", dict(maxiter=50)), ("geomed", dict(maxiter=50, compat=False)),
                                       ("centeredclipping", dict(tau=0.05, n_iter=3)),
-                                      ("fltrust", dict(trusted_index=4))])
+                                      ("fltrust", dict(trusted_index=4)), ("autogm", dict(maxiter=20))])
 def test_aggregators_device_solve_equals_host_solve(name, kws, monkeypatch):
     import blades_b200.aggregators as A
     cls = {k.lower(): v for k, v in vars(A).items() if isinstance(v, type)}[name]

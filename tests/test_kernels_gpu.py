@@ -365,7 +365,7 @@ def test_wgrad_padded_rows():
 
 @pytest.mark.parametrize("agg,attack", [("trimmedmean", "alie"), ("median", "ipm"), ("mean", None), ("trimmedmean", "labelflipping"),
                                         ("krum", "labelflipping"), ("multikrum", "alie"), ("geomed", None),
-                                        ("centeredclipping", "signflipping")])
+                                        ("centeredclipping", "signflipping"), ("autogm", "ipm")])
 def test_whole_round_graph_equals_eager(agg, attack, tmp_path, monkeypatch):
     """Rounds 3+ replay one captured CUDA graph (train + fused attack/aggregate/server step): same result as eager.
     The Gram-based aggregators join the graph because their solvers run on the device (ops/gram_solve)."""
