@@ -446,7 +446,12 @@ client_bn_nhwc_bwd_cl_kernel(const __grid_constant__ ClientBNParams p) {
         for (int r = rg; r < Rc; r += GROUPS) {
             float4 g = __ldcs(&gb[(long long)r * rs]);
             const float4 v = __ldcs(&xb[(long long)r * rs]);
-            if (p.relu) g = bn_relu_mask(g, remask ? bn_pre(v, fg, fsh) : __ldcs(&ab[(long long)r * rs]));
+            if (p.relu) {
+                float4 a;
+                if (remask) a = bn_pre(v, fg, fsh);
+                else a = __ldcs(&ab[(long long)r * rs]);
+                g = bn_relu_mask(g, a);
+            }
             if (mb != nullptr) mb[(long long)r * rs] = g;
             const float4 xh = make_float4((v.x - mean.x) * rstd.x, (v.y - mean.y) * rstd.y, (v.z - mean.z) * rstd.z,
                                           (v.w - mean.w) * rstd.w);

@@ -167,14 +167,10 @@ coord_select_kernel(const __grid_constant__ SelectParams p) {
 // Partition-only trimmed mean (select_part_core.cuh): n_real == NP == 4 * trim_b and (no virtual rows or f >= b)
 // -- the "20 % attackers, Trimmedmean(nb = f)" family (N = 10k clients: 8k honest rows, b = 2k).  Two half-size
 // sorts + two bitonic splits instead of one full network: ~21 % fewer FMNMX on the pipe that bounds this kernel.
-// Launch bounds of the partition kernel.  select_part_core.cuh can run the two half sorts as ONE rolled code copy
-// (ncu's top stall is "no_instruction"); with the exchange of the halves between the passes and the 128-register
-// budget it needs, that form measured slower (1.02 vs 0.95 ms), so kRoll stays off.
-template <int NP> struct PartBounds {
-    static constexpr bool kRoll = false;      // measured: 1.02 ms rolled vs 0.95 ms unrolled at the headline shape
-    static constexpr int kThreads = SelectBlock<NP>::kMax;
-    static constexpr int kBlocks = 1;
-};
+// select_part_core.cuh can run the two half sorts as ONE rolled code copy (ncu's top stall of this kernel is
+// "no_instruction"); with the exchange of the halves between the passes and the 128-register budget it then needs,
+// that form measured slower (1.02 vs 0.95 ms at the headline shape), so it stays off.
+constexpr bool kSelectRollHalves = false;
 
 template <int NP, int MIX>
 __global__ void __launch_bounds__(SelectBlock<NP>::kMax)
@@ -198,7 +194,7 @@ coord_select_part_kernel(const __grid_constant__ SelectParams p) {
     float m = 0.f;
     if (f > 0) m = p.n_stat == NP ? bl_virtual_value_all<NP>(a, b, total, p.virt_kind, p.virt_param)
                                   : bl_virtual_value<NP>(a, b, p.n_stat, p.virt_kind, p.virt_param);
-    bl_epilogue_store(p.ep, c, bl_trimmed_partition<NP, MIX, PartBounds<NP>::kRoll>(a, b, m, f));
+    bl_epilogue_store(p.ep, c, bl_trimmed_partition<NP, MIX, kSelectRollHalves>(a, b, m, f));
 }
 
 // ---------------------------------------------------------------------------------------------

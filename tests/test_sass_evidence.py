@@ -89,7 +89,10 @@ def test_hot_kernels_do_not_spill():
             if "part_stage" in name:          # opt-in bulk-copy staged form (measured slower): one 8-byte frame slot
                 assert int(stack) <= 16 and int(local) == 0, (name, stack, local)
                 continue
-            if "coord_select_part_kernel" in name:   # rolled half sorts: ptxas keeps up to 6 values in a 24 B frame
+            if "client_bn_nhwc_bwd_cl_kernel" in name:   # 64 registers + one 8-byte frame slot (cluster handle), no local memory
+                assert int(stack) <= 16 and int(local) == 0, (name, stack, local)
+                continue
+            if "coord_select_part_kernel" in name:   # ptxas may keep a few values in a <= 32 B frame at some sizes
                 assert int(stack) <= 32 and int(local) == 0, (name, stack, local)
                 continue
             assert int(stack) == 0 and int(local) == 0, (name, stack, local)
