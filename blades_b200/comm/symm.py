@@ -62,6 +62,7 @@ class SymmetricUpdates:
         from ..ops import nvls
         nvls.zero_(self.buf)
         self.handle = symm_mem.rendezvous(self.buf, dist.group.WORLD)
+        self.barrier_timeout_ms = max(0, int(os.environ.get("BLADES_BARRIER_TIMEOUT_MS", "120000")))
         self.base_ptrs: List[int] = [int(p) for p in self.handle.buffer_ptrs]
         self.off_agg = self.nmax * self.ld
         self.off_theta = self.off_agg + self.ld
@@ -140,4 +141,8 @@ class SymmetricUpdates:
         return self.col_ranges[self.world.rank]
 
     def barrier(self, channel: int = 0) -> None:
-        self.handle.barrier(channel=channel)
+        """Device barrier over the signal pads (stream ordered, capturable).  Failure detection: a rank that died or
+        never arrives would leave the others spinning forever inside the barrier kernel; with a timeout
+        (``BLADES_BARRIER_TIMEOUT_MS``, default 120 000, 0 = wait forever) the waiting kernels trap instead, the CUDA
+        error surfaces at the next synchronisation and the job aborts instead of hanging the node."""
+        self.handle.barrier(channel=channel, timeout_ms=self.barrier_timeout_ms)
