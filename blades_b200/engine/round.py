@@ -13,9 +13,13 @@ k SGD steps, 2x flat concat to CPU              | clients, wgrad epilogue writes
                                                 | worker model, one fused diff kernel per client
 gather N CPU vectors, torch.stack               | rows already sit in U_g[n_local, d]
                                                 | (NVLink-addressable symmetric memory)
-f attacker callbacks on CPU                     | virtual rows inside the aggregation kernel
-aggregator on CPU [N,d]                         | fused pull-mode kernels / tcgen05 Gram
+f attacker callbacks on CPU                     | virtual rows inside the aggregation kernel;
+                                                | row-local attackers (Noise) on the owning rank
+aggregator on CPU [N,d]                         | fused kernels per coordinate window, started on a
+                                                | side stream while the backward pass still runs
+                                                | (_AggPipeline); tcgen05 Gram + on-device solvers
 per-param python loop + optimizer.step          | theta += lr*agg in the kernel epilogue
+                                                | (multimem.st to every replica)
 """
 from __future__ import annotations
 

@@ -1,12 +1,20 @@
 """``ShardedMatrix``: the update matrix spread over G trainer shards, rows in NVLink-addressable
 symmetric memory, aggregation coordinate-sharded.
 
-Every primitive is ONE pull-mode kernel per rank: rank g owns coordinates ``[c_g, c_{g+1})``, its
-CTAs read that coordinate range of EVERY row -- local rows from HBM, peer rows with plain global
-loads / TMA on NVLink-mapped pointers -- reduce in registers / tensor cores, and store the result
-range into every replica (``agg`` and, when the server step is fused, ``theta``).  The reference's
-gather (Ray pickles -> torch.stack, simulator.py:235 + mean.py:23) and broadcast (model pickled to
-every actor, simulator.py:222-233) therefore never exist as separate steps.
+Every primitive is ONE kernel per rank: rank g owns coordinates ``[c_g, c_{g+1})`` (of the whole
+vector, or of the window of it this matrix object covers -- pipelined aggregation), its CTAs read
+that coordinate range of EVERY row, reduce in registers / tensor cores, and store the result range
+into every replica (``agg`` and, when the server step is fused, ``theta``; one ``multimem.st`` per
+value when the fabric has a multicast object).  The rows reach the kernel in one of two ways:
+
+* pull: local rows from HBM, peer rows with plain global loads / TMA on NVLink-mapped pointers;
+* push (``push_plan``): every rank DMAs its rows' slice of the other ranks' ranges into their
+  ``recv`` landing zones with copy-engine 2-D copies, the kernel then reads local memory only.
+
+The reference's gather (Ray pickles -> torch.stack, simulator.py:235 + mean.py:23) and broadcast
+(model pickled to every actor, simulator.py:222-233) therefore never exist as separate steps.
+Gram partials are summed inside the NVSwitch (``SymmetricUpdates.reduce_scratch``) and handed to
+the on-device solvers (``ops.gram_solve``) without leaving device memory.
 """
 from __future__ import annotations
 
