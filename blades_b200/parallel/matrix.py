@@ -168,6 +168,17 @@ class LocalMatrix(UpdateMatrix):
             return self.out_buffer
         return torch.empty(self.n_cols, device=device, dtype=torch.float32)
 
+    def _windowed(self, full: torch.Tensor) -> torch.Tensor:
+        """CPU oracle of a windowed primitive: the full-width result restricted to this object's window, written into
+        the round's shared result vector (coordinates outside the window are left to the other chunks)."""
+        if self.window is None:
+            return full
+        c0, c1 = self._cols()
+        if self.out_buffer is None:
+            self.out_buffer = torch.zeros_like(full)
+        self.out_buffer[c0:c1] = full[c0:c1]
+        return self.out_buffer
+
     def _epilogue(self, out: torch.Tensor):
         from ..ops import select as _s
         if self.server_step is not None and self.theta is not None:
@@ -207,12 +218,12 @@ class LocalMatrix(UpdateMatrix):
         res = (w.to(data.device, torch.float64)[:, None] * data.double()).sum(0)
         if extra is not None and extra_weight != 0.0:
             res = res + extra_weight * extra.to(res.device, torch.float64)
-        return res.to(data.dtype)
+        return self._windowed(res.to(data.dtype))
 
     def mean(self) -> torch.Tensor:
         if self.use_kernels:
             return super().mean()
-        return self.rows().mean(dim=0)
+        return self._windowed(self.rows().mean(dim=0))
 
     def trimmed_mean(self, b: int) -> torch.Tensor:
         n = self.n_rows
@@ -222,9 +233,9 @@ class LocalMatrix(UpdateMatrix):
             return self._select_kernel(0, b)
         data = self.rows()
         if b == 0:
-            return data.mean(0)
+            return self._windowed(data.mean(0))
         srt = data.sort(dim=0).values
-        return srt[b: n - b].mean(dim=0)
+        return self._windowed(srt[b: n - b].mean(dim=0))
 
     def _select_kernel(self, mode: int, b: int) -> torch.Tensor:
         from ..ops import select as _s
@@ -248,7 +259,7 @@ class LocalMatrix(UpdateMatrix):
         data = self.rows()
         n = self.n_rows
         srt = data.sort(dim=0).values
-        return (srt[(n - 1) // 2] + srt[n // 2]) * 0.5
+        return self._windowed((srt[(n - 1) // 2] + srt[n // 2]) * 0.5)
 
     def gram(self, extra: Optional[torch.Tensor] = None) -> np.ndarray:
         data = self.rows()

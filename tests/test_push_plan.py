@@ -108,3 +108,25 @@ def test_checkpoint_plain_roundtrip_is_weights_only_loadable(tmp_path):
     assert (cur2["client_3"]["perm"] == cur["client_3"]["perm"]).all() and cur2["client_3"]["pos"] == 4
     np.random.set_state(rng2["numpy"])
     random.setstate(rng2["python"])
+
+
+def test_windowed_primitives_tile_to_the_whole_result_on_the_cpu_oracle():
+    """The coordinate-wise primitives of a matrix object restricted to a window write only that window of the shared
+    result vector; windows that tile [0, d) reproduce the unwindowed result (the contract the pipelined GPU rounds
+    rely on), with and without virtual attack rows."""
+    import torch
+    from blades_b200.parallel.matrix import LocalMatrix, VirtualRows
+    torch.manual_seed(0)
+    n, d = 12, 1000
+    data = torch.randn(n, d)
+    windows = [(640, d), (256, 640), (0, 256)]
+    for virt in (None, VirtualRows("alie", 0.5, [0, 1, 2]), VirtualRows("ipm", 2.0, [0, 1])):
+        for op in (lambda m: m.trimmed_mean(3), lambda m: m.median(), lambda m: m.mean(),
+                   lambda m: m.combine(torch.linspace(0.0, 1.0, n))):
+            whole = op(LocalMatrix(data.clone(), virtual=virt))
+            out = None
+            for k, win in enumerate(windows):
+                m = LocalMatrix(data.clone(), virtual=virt)
+                m.window, m.chunk, m.last_chunk, m.out_buffer = win, k, k == len(windows) - 1, out
+                out = op(m)
+            assert torch.allclose(out, whole, atol=0, rtol=0)
